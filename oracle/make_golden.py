@@ -1,0 +1,57 @@
+"""Generate tests/golden/model_*.npz from the REAL reference (run in the authoring container only).
+
+    python -m oracle.make_golden            # needs /root/reference
+
+For each case the unmodified reference model (imported through oracle/ref_shim.py) is run on CPU in
+fp32 and in fp64 on the seeded fixture of oracle/fixtures.py; the predictions are stored together with
+the fixture parameters so tests can rebuild the exact inputs anywhere (TEST INFRASTRUCTURE).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+
+from oracle import cotr_oracle, fixtures, ref_shim  # noqa: E402
+
+# name: (weight_seed, qk_gain, head_gain, input_seed, batch, n_queries)
+CASES = {
+    "model_b1_q1024": (0, 3.0, 1.35, 1, 1, 1024),      # BASELINE.json configs[1] shape
+    "model_b2_q100": (0, 3.0, 1.35, 2, 2, 100),        # ragged Q (not a multiple of any tile)
+    "model_b3_q1": (0, 3.0, 1.35, 3, 3, 1),            # default engine step shape (one query per context)
+    "model_peaked_b1_q257": (7, 4.0, 1.0, 4, 1, 257),  # sharper attention, FasterSparseEngine max load + pilot
+}
+
+
+def main():
+    torch.set_grad_enabled(False)
+    out_dir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (wseed, qk, hg, iseed, b, q) in CASES.items():
+        sd = fixtures.make_state_dict(wseed, qk, hg)
+        img, queries = fixtures.make_inputs(iseed, b, q)
+        model = ref_shim.build_reference_model(sd)
+        ref32 = model(torch.from_numpy(img), torch.from_numpy(queries))["pred_corrs"].numpy()
+        model = model.double()
+        ref64 = model(torch.from_numpy(img).double(), torch.from_numpy(queries).double())["pred_corrs"].numpy()
+        o64, inter = cotr_oracle.forward(sd, img, queries, torch.float64, return_intermediates=True)
+        o32 = cotr_oracle.forward(sd, img, queries, torch.float32)
+        d_oracle = float(np.abs(o64.numpy() - ref64).max())
+        print(f"{name}: std over queries {ref64.std(axis=1).max():.4f}  |ref32-ref64| {np.abs(ref32 - ref64).max():.2e}  "
+              f"|oracle64-ref64| {d_oracle:.2e}  |oracle32-ref32| {np.abs(o32.numpy() - ref32).max():.2e}")
+        np.savez_compressed(
+            os.path.join(out_dir, name + ".npz"),
+            params=np.array([wseed, qk, hg, iseed, b, q], dtype=np.float64),
+            ref_pred_fp32=ref32.astype(np.float32), ref_pred_fp64=ref64.astype(np.float64),
+            oracle_vs_ref_fp64=np.array(d_oracle),
+            feat_rms=np.array(float(inter["feat"].pow(2).mean().sqrt())),
+            mem_head=inter["mem"][0, :4, :16].numpy(), hs_head=inter["hs"][0, :4, :16].numpy(),
+        )
+
+
+if __name__ == "__main__":
+    main()
