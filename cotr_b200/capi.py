@@ -1,0 +1,214 @@
+"""ctypes binding of the C ABI declared in include/cotr_b200.h.
+
+There is deliberately no CPU fallback: if the shared library is missing or no sm_100 GPU is visible the calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcotr_b200.so")
+
+_lib = None
+
+
+class CotrTensor(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.POINTER(ctypes.c_float)),
+                ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * 4)]
+
+
+class TestGemmDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "path", "M", "N", "K", "a_mode", "lda", "H", "W", "C", "OH", "OW", "KH", "KW", "stride", "pad",
+        "relu", "add_period", "ld_add", "ldr", "ldc")]
+
+
+# name -> (restype, argtypes); every symbol include/cotr_b200.h declares
+_PROTOTYPES = {
+    "cotr_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(CotrTensor), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "cotr_destroy": (None, [ctypes.c_void_p]),
+    "cotr_context_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "cotr_context_destroy": (None, [ctypes.c_void_p]),
+    "cotr_encode_context": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "cotr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "cotr_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "cotr_debug_read": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
+    "cotr_set_gemm_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cotr_test_gemm": (ctypes.c_int, [ctypes.POINTER(TestGemmDesc)] + [ctypes.c_void_p] * 8),
+    "cotr_test_attention": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int]),
+    "cotr_debug_set_variant": (None, [ctypes.c_int]),
+    "cotr_last_error": (ctypes.c_char_p, []),
+    "cotr_version": (ctypes.c_char_p, []),
+}
+
+
+def lib():
+    """The loaded shared library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m cotr_b200.build` "
+                               "(cotr_b200 has no CPU / PyTorch fallback by design)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().cotr_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {last_error()}")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class NativeContext:
+    """Decoder K/V cache of up to `max_pairs` encoded image pairs (cotr_context)."""
+
+    def __init__(self, model, max_pairs):
+        self.model = model
+        self.max_pairs = max_pairs
+        self.pairs = 0
+        h = ctypes.c_void_p()
+        check(lib().cotr_context_create(model.handle, int(max_pairs), ctypes.byref(h)), "cotr_context_create")
+        self.handle = h
+
+    def close(self):
+        if self.handle is not None and self.model.handle is not None:
+            lib().cotr_context_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NativeModel:
+    """Owner of a `cotr_model` handle built from a reference-schema state dict (CPU fp32 tensors / arrays)."""
+
+    def __init__(self, state_dict, device_index):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cotr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        names, arrays = [], []
+        for k, v in state_dict.items():
+            a = v.detach().to("cpu", torch.float32).contiguous().numpy() if isinstance(v, torch.Tensor) else np.ascontiguousarray(v, np.float32)
+            if a.ndim > 4:
+                continue
+            names.append(k.encode())
+            arrays.append(a)
+        arr = (CotrTensor * len(arrays))()
+        for i, (n, a) in enumerate(zip(names, arrays)):
+            arr[i].name = n
+            arr[i].data = a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+            arr[i].ndim = a.ndim
+            for d in range(a.ndim):
+                arr[i].shape[d] = a.shape[d]
+        h = ctypes.c_void_p()
+        self.handle = None
+        self.device_index = int(device_index)
+        check(lib().cotr_create(self.device_index, arr, len(arrays), ctypes.byref(h)), "cotr_create")
+        self.handle = h
+
+    # ---- calls ------------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device_index).cuda_stream)
+
+    def forward(self, img, queries):
+        B, Q = queries.shape[0], queries.shape[1]
+        pred = torch.empty((B, Q, 2), dtype=torch.float32, device=img.device)
+        check(lib().cotr_forward(self.handle, _ptr(img), _ptr(queries), B, Q, _ptr(pred), self._stream()), "cotr_forward")
+        return pred
+
+    def encode_context(self, img, ctx):
+        check(lib().cotr_encode_context(self.handle, _ptr(img), img.shape[0], ctx.handle, self._stream()), "cotr_encode_context")
+        ctx.pairs = img.shape[0]
+
+    def decode(self, ctx, queries):
+        B, Q = queries.shape[0], queries.shape[1]
+        pred = torch.empty((B, Q, 2), dtype=torch.float32, device=queries.device)
+        check(lib().cotr_decode(self.handle, ctx.handle, _ptr(queries), B, Q, _ptr(pred), self._stream()), "cotr_decode")
+        return pred
+
+    def forward_host(self, img_np, queries_np, out_np=None):
+        """Host buffers in, host buffer out (H2D + forward + D2H inside the C call)."""
+        B, Q = queries_np.shape[0], queries_np.shape[1]
+        if out_np is None:
+            out_np = np.empty((B, Q, 2), dtype=np.float32)
+        check(lib().cotr_forward_host(self.handle, ctypes.c_void_p(img_np.ctypes.data), ctypes.c_void_p(queries_np.ctypes.data),
+                                      B, Q, ctypes.c_void_p(out_np.ctypes.data)), "cotr_forward_host")
+        return out_np
+
+    def set_gemm_path(self, path):
+        check(lib().cotr_set_gemm_path(self.handle, int(path)), "cotr_set_gemm_path")
+
+    def last_launch_count(self):
+        return lib().cotr_last_launch_count(self.handle)
+
+    def debug_read(self, name, n_elems):
+        out = np.empty(int(n_elems), dtype=np.float32)
+        n = lib().cotr_debug_read(self.handle, name.encode(), ctypes.c_void_p(out.ctypes.data), int(n_elems))
+        if n < 0:
+            raise RuntimeError(f"cotr_debug_read({name}) failed")
+        return out[:n]
+
+    def close(self):
+        if self.handle is not None:
+            lib().cotr_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def test_gemm(path, A, w_host, *, bias=None, addmat=None, add_period=1, residual=None, relu=False, ln=None,
+              a_mode=0, conv=None, M=None, ldc=None):
+    """Kernel-level hook: out = epilogue(A W^T).  A and optional epilogue operands are CUDA fp32 tensors."""
+    N, K = w_host.shape
+    d = TestGemmDesc()
+    d.path = path
+    d.N, d.K = N, K
+    d.a_mode = a_mode
+    if a_mode == 0:
+        d.M = A.shape[0] if M is None else M
+        d.lda = A.stride(0)
+    else:
+        d.M = M
+        for k_, v_ in conv.items():
+            setattr(d, k_, v_)
+        d.lda = conv.get("C", 0) if a_mode != 3 else A.shape[-1]
+    d.relu = int(relu)
+    d.add_period = add_period
+    d.ld_add = addmat.stride(0) if addmat is not None else 0
+    d.ldr = residual.stride(0) if residual is not None else 0
+    d.ldc = N if ldc is None else ldc
+    out = torch.zeros((d.M, d.ldc), dtype=torch.float32, device=A.device)
+    w_np = np.ascontiguousarray(w_host, np.float32)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    check(lib().cotr_test_gemm(ctypes.byref(d), p(A), ctypes.c_void_p(w_np.ctypes.data), p(bias), p(addmat), p(residual),
+                               p(ln[0]) if ln else None, p(ln[1]) if ln else None, p(out)), "cotr_test_gemm")
+    return out
+
+
+def test_attention(path, q, k, v, nq, npairs):
+    out = torch.zeros_like(q)
+    check(lib().cotr_test_attention(path, _ptr(q), _ptr(k), _ptr(v), _ptr(out), nq, npairs), "cotr_test_attention")
+    return out

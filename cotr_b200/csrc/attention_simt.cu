@@ -1,0 +1,101 @@
+// fp32 SIMT attention over the 512-token context: exact softmax(q k^T) v per head.
+// Numerical cross-check path for attention_tc.cu; also the fallback for launches with very few query rows.
+#include "common.cuh"
+
+namespace cotr {
+
+namespace {
+
+constexpr int kRowsPerCta = 64;
+constexpr int kWarps = 8;
+constexpr int kKStride = kHeadDim + 1;   // padded: lane j reads key (j + 32 i) without bank conflicts
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) attention_simt_kernel(const AttnParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* Ks = smem;                                  // [512][33]
+    float* Vs = Ks + kTokens * kKStride;               // [512][32]
+    float* Qs = Vs + kTokens * kHeadDim;               // [kWarps][32]
+
+    const int head = blockIdx.y;
+    const int pair_local = blockIdx.z;
+    const int row_begin = blockIdx.x * kRowsPerCta;
+    const int row_end = min(row_begin + kRowsPerCta, p.nq);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
+    for (int idx = tid; idx < kTokens * (kHeadDim / 4); idx += blockDim.x) {
+        const int key = idx >> 3, d4 = (idx & 7) * 4;
+        const float4 kk = __ldg(reinterpret_cast<const float4*>(p.k + (kv_row0 + key) * p.ldk + head * kHeadDim + d4));
+        const float4 vv = __ldg(reinterpret_cast<const float4*>(p.v + (kv_row0 + key) * p.ldv + head * kHeadDim + d4));
+        float* kd = Ks + key * kKStride + d4;
+        kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
+        *reinterpret_cast<float4*>(Vs + key * kHeadDim + d4) = vv;
+    }
+    __syncthreads();
+
+    float* qs = Qs + warp * kHeadDim;
+    for (int i = row_begin + warp; i < row_end; i += kWarps) {
+        const size_t r = (size_t)pair_local * p.nq + i;
+        qs[lane] = __ldg(p.q + r * p.ldq + head * kHeadDim + lane);
+        __syncwarp();
+        float s[kTokens / 32];
+#pragma unroll
+        for (int t = 0; t < kTokens / 32; ++t) s[t] = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < kHeadDim; ++d) {
+            const float qd = qs[d];
+#pragma unroll
+            for (int t = 0; t < kTokens / 32; ++t) s[t] = fmaf(qd, Ks[(lane + 32 * t) * kKStride + d], s[t]);
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int t = 1; t < kTokens / 32; ++t) mx = fmaxf(mx, s[t]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int t = 0; t < kTokens / 32; ++t) { s[t] = expf(s[t] - mx); sum += s[t]; }
+        sum = warp_sum(sum);
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < kTokens / 32; ++t) {
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const float pj = __shfl_sync(0xffffffffu, s[t], l);
+                acc = fmaf(pj, Vs[(l + 32 * t) * kHeadDim + lane], acc);
+            }
+        }
+        p.out[r * p.ldo + head * kHeadDim + lane] = acc / sum;
+        __syncwarp();
+    }
+}
+
+constexpr size_t kSmemBytes = (size_t)(kTokens * kKStride + kTokens * kHeadDim + kWarps * kHeadDim) * sizeof(float);
+
+}  // namespace
+
+int launch_attention_simt(const AttnParams& p, cudaStream_t s) {
+    if (p.nq <= 0 || p.npairs <= 0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        COTR_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        configured = true;
+    }
+    COTR_CHECK(p.npairs <= 65535, "attention: too many pairs in one launch (%d)", p.npairs);
+    dim3 grid((p.nq + kRowsPerCta - 1) / kRowsPerCta, kHeads, p.npairs);
+    attention_simt_kernel<<<grid, kWarps * 32, kSmemBytes, s>>>(p);
+    COTR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cotr

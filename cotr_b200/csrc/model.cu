@@ -1,0 +1,854 @@
+// Model state, weight packing, workspace and the forward schedule behind the C ABI (include/cotr_b200.h).
+//
+// Reference lines restated by each stage are cited inline (paths relative to the reference root).
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cotr_b200.h"
+#include "common.cuh"
+
+namespace cotr {
+
+extern int g_tc_variant;
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+constexpr int kDecodeChunkRows = 32768;   // decoder rows processed per pass (rows are independent, so chunking is exact)
+constexpr int kKvCols = kDecLayers * 2 * kDModel;    // 3072: [layer][K | V][256]
+constexpr int kQpCols = kDecLayers * kDModel;        // 1536
+
+struct DevConv {
+    float* w = nullptr;    // [cout][kh][kw][cin], FrozenBN scale folded in
+    void* wtc = nullptr;   // tensor-core image of w
+    float wtc_scale = 1.f; // accumulator scale that undoes the image's power-of-two pre-scaling
+    float* b = nullptr;    // FrozenBN shift
+    int cout = 0, cin = 0, kh = 1, kw = 1, stride = 1, pad = 0;
+};
+
+struct DevLinear {
+    float* w = nullptr;    // [N][K]
+    void* wtc = nullptr;
+    float wtc_scale = 1.f;
+    float* b = nullptr;    // [N] or null
+    int n = 0, k = 0;
+};
+
+struct Block {
+    DevConv c1, c2, c3, ds;
+    bool has_ds = false;
+};
+
+struct EncLayer {
+    DevLinear qkv;         // [768][256]; q rows pre-scaled by head_dim^-0.5; bias folded into add_qkv
+    float* add_qkv = nullptr;   // [512][768] = [ (pos Wq^T + bq) s | pos Wk^T + bk | bv ]
+    DevLinear o, l1, l2;
+    float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+struct DecLayer {
+    DevLinear q;           // [256][256] pre-scaled, no bias (bias lives in the qpos projection)
+    DevLinear o, l1, l2;
+    float *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+};
+
+struct Workspace {
+    int cap_pairs = 0;
+    int cap_rows = 0;
+    // backbone (per image sizes x 2*cap_pairs)
+    float *stem = nullptr, *bx = nullptr, *by = nullptr, *bt1 = nullptr, *bt2 = nullptr, *bds = nullptr;
+    // encoder
+    float *src = nullptr, *xa = nullptr, *xb = nullptr, *qkv = nullptr, *ao = nullptr, *ffh = nullptr, *tmp = nullptr;
+    // decoder
+    float *qpos = nullptr, *qp = nullptr, *t = nullptr, *qb = nullptr, *dao = nullptr, *dtmp = nullptr, *dh = nullptr,
+          *hs = nullptr, *hd1 = nullptr, *hd2 = nullptr;
+    // host-buffer entry point staging
+    float *img_stage = nullptr, *q_stage = nullptr, *pred_stage = nullptr;
+    size_t img_stage_elems = 0, q_stage_elems = 0;
+};
+
+}  // namespace
+}  // namespace cotr
+
+struct cotr_context {
+    cotr_model* model = nullptr;
+    float* kv = nullptr;        // [max_pairs * 512][3072]
+    int max_pairs = 0;
+    int pairs = 0;              // pairs encoded by the last cotr_encode_context
+};
+
+struct cotr_model {
+    int device = 0;
+    int gemm_path = 0;          // 0 = tcgen05, 1 = fp32 SIMT
+    int launches = 0;
+    std::vector<void*> allocs;
+    cotr::DevConv stem;
+    std::vector<cotr::Block> blocks;
+    cotr::DevLinear proj;
+    cotr::EncLayer enc[cotr::kEncLayers];
+    cotr::DevLinear kv_all;     // [3072][256], bias folded into add_kv
+    float* add_kv = nullptr;    // [512][3072]
+    cotr::DevLinear qpos_all;   // [1536][256] pre-scaled, bias pre-scaled
+    cotr::DecLayer dec[cotr::kDecLayers];
+    float *dec_norm_g = nullptr, *dec_norm_b = nullptr;
+    cotr::DevLinear head[3];
+    float* pos = nullptr;       // [512][256] grid position embedding
+    cotr::Workspace ws;
+    cotr_context* own_ctx = nullptr;
+    cudaStream_t host_stream = nullptr;
+    const float* last_feat = nullptr;
+    const float* last_mem = nullptr;
+    int last_pairs = 0, last_rows = 0;
+};
+
+namespace cotr {
+namespace {
+
+// ----------------------------------------------------------------------------------------------
+// weight lookup / upload helpers
+// ----------------------------------------------------------------------------------------------
+struct TensorMap {
+    std::map<std::string, const cotr_tensor*> m;
+    const cotr_tensor* get(const std::string& name, std::initializer_list<int64_t> shape) const {
+        auto it = m.find(name);
+        if (it == m.end()) { set_error("cotr_create: missing tensor '%s'", name.c_str()); return nullptr; }
+        const cotr_tensor* t = it->second;
+        if (t->ndim != (int)shape.size()) { set_error("cotr_create: '%s' has ndim %d, expected %zu", name.c_str(), t->ndim, shape.size()); return nullptr; }
+        int i = 0;
+        for (int64_t s : shape) {
+            if (t->shape[i] != s) { set_error("cotr_create: '%s' dim %d is %lld, expected %lld", name.c_str(), i, (long long)t->shape[i], (long long)s); return nullptr; }
+            ++i;
+        }
+        if (!t->data) { set_error("cotr_create: '%s' has a null data pointer", name.c_str()); return nullptr; }
+        return t;
+    }
+};
+
+int dev_alloc(cotr_model* m, void** p, size_t bytes) {
+    COTR_CHECK_CUDA(cudaMalloc(p, bytes ? bytes : 4));
+    m->allocs.push_back(*p);
+    return 0;
+}
+
+int upload(cotr_model* m, const std::vector<float>& h, float** d) {
+    if (dev_alloc(m, (void**)d, h.size() * sizeof(float))) return 1;
+    COTR_CHECK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int upload_tc(cotr_model* m, const std::vector<float>& w, int N, int K, void** d, float* acc_scale) {
+    const size_t bytes = tc_weight_bytes(N, K);
+    std::vector<uint8_t> img(bytes);
+    *acc_scale = tc_pack_weight(w.data(), N, K, img.data());
+    if (dev_alloc(m, d, bytes)) return 1;
+    COTR_CHECK_CUDA(cudaMemcpy(*d, img.data(), bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int make_linear(cotr_model* m, const std::vector<float>& w, const std::vector<float>* b, int N, int K, DevLinear* out) {
+    out->n = N; out->k = K;
+    if (upload(m, w, &out->w)) return 1;
+    if (upload_tc(m, w, N, K, &out->wtc, &out->wtc_scale)) return 1;
+    if (b) { if (upload(m, *b, &out->b)) return 1; }
+    return 0;
+}
+
+// backbone.py:46-56 folded into the conv: w' = w * s[o], shift = b - rm * s, s = weight * (rv + 1e-5)^-1/2.
+int make_conv(cotr_model* m, const TensorMap& tm, const std::string& conv, const std::string& bn,
+              int cout, int cin, int kh, int kw, int stride, int pad, DevConv* out) {
+    const cotr_tensor* w = tm.get(conv + ".weight", {cout, cin, kh, kw});
+    const cotr_tensor* g = tm.get(bn + ".weight", {cout});
+    const cotr_tensor* b = tm.get(bn + ".bias", {cout});
+    const cotr_tensor* rm = tm.get(bn + ".running_mean", {cout});
+    const cotr_tensor* rv = tm.get(bn + ".running_var", {cout});
+    if (!w || !g || !b || !rm || !rv) return 1;
+    std::vector<float> wf((size_t)cout * kh * kw * cin), bf(cout);
+    for (int o = 0; o < cout; ++o) {
+        const double s = (double)g->data[o] / std::sqrt((double)rv->data[o] + 1e-5);
+        bf[o] = (float)((double)b->data[o] - (double)rm->data[o] * s);
+        for (int c = 0; c < cin; ++c)
+            for (int y = 0; y < kh; ++y)
+                for (int x = 0; x < kw; ++x)
+                    wf[(((size_t)o * kh + y) * kw + x) * cin + c] =
+                        (float)((double)w->data[(((size_t)o * cin + c) * kh + y) * kw + x] * s);
+    }
+    out->cout = cout; out->cin = cin; out->kh = kh; out->kw = kw; out->stride = stride; out->pad = pad;
+    if (upload(m, wf, &out->w)) return 1;
+    if (upload_tc(m, wf, cout, kh * kw * cin, &out->wtc, &out->wtc_scale)) return 1;
+    if (upload(m, bf, &out->b)) return 1;
+    return 0;
+}
+
+std::vector<float> to_vec(const cotr_tensor* t, size_t n, size_t offset = 0) {
+    return std::vector<float>(t->data + offset, t->data + offset + n);
+}
+
+int upload_vec(cotr_model* m, const TensorMap& tm, const std::string& name, int n, float** d) {
+    const cotr_tensor* t = tm.get(name, {n});
+    if (!t) return 1;
+    return upload(m, to_vec(t, n), d);
+}
+
+// position_encoding.py:60-72 for the all-False mask of the 16x32 grid, evaluated like the reference in fp32.
+std::vector<float> grid_position_table() {
+    std::vector<float> pos((size_t)kTokens * kDModel);
+    for (int i = 0; i < 16; ++i)
+        for (int j = 0; j < 32; ++j) {
+            const float y = ((float)(i + 1) - 0.5f) / ((float)16 + 1e-6f);
+            const float x = ((float)(j + 1) - 0.5f) / ((float)32 + 1e-6f);
+            float* row = pos.data() + (size_t)(i * 32 + j) * kDModel;
+            for (int k = 1; k <= 64; ++k) {
+                const float kpi = (float)((double)k * 3.14159265358979323846);
+                const float ax = kpi * x, ay = kpi * y;
+                row[2 * (k - 1) + 0] = (float)std::sin((double)ax);
+                row[2 * (k - 1) + 1] = (float)std::sin((double)ay);
+                row[128 + 2 * (k - 1) + 0] = (float)std::cos((double)ax);
+                row[128 + 2 * (k - 1) + 1] = (float)std::cos((double)ay);
+            }
+        }
+    return pos;
+}
+
+// ----------------------------------------------------------------------------------------------
+// launch helpers (all kernel launches of the forward go through these, so they can be counted)
+// ----------------------------------------------------------------------------------------------
+struct Run {
+    cotr_model* m;
+    cudaStream_t s;
+};
+
+GemmParams gemm_base(int M, int N, int K, const float* A, int lda, const float* W, const void* Wtc, float wtc_scale,
+                     float* out, int ldc) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.acc_scale = wtc_scale;
+    p.M = M; p.N = N; p.K = K;
+    p.A = A; p.a_mode = A_ROWMAJOR; p.lda = lda;
+    p.Wt = W; p.Wtc = Wtc;
+    p.out = out; p.ldc = ldc;
+    p.add_period = 1;
+    return p;
+}
+
+int run_gemm(const Run& r, GemmParams p, float* ln_scratch) {
+    // The tensor-core GEMM fuses LayerNorm into its epilogue; the SIMT path runs it as a separate kernel.
+    if (r.m->gemm_path == 0) {
+        r.m->launches++;
+        return launch_gemm_tc(p, r.s);
+    }
+    const float* g = p.ln_gamma;
+    const float* b = p.ln_beta;
+    float* final_out = p.out;
+    if (g) {
+        COTR_CHECK(p.N == kDModel && p.ldc == kDModel && ln_scratch != nullptr, "run_gemm: LayerNorm epilogue needs N = 256");
+        p.ln_gamma = nullptr; p.ln_beta = nullptr;
+        p.out = ln_scratch;
+    }
+    r.m->launches++;
+    if (launch_gemm_simt(p, r.s)) return 1;
+    if (g) {
+        r.m->launches++;
+        if (launch_layernorm(ln_scratch, nullptr, g, b, final_out, p.M, r.s)) return 1;
+    }
+    return 0;
+}
+
+int run_linear(const Run& r, const DevLinear& L, int M, const float* A, int lda, float* out, int ldc, bool relu,
+               const float* residual = nullptr, int ldr = 0, const float* ln_g = nullptr, const float* ln_b = nullptr,
+               float* ln_scratch = nullptr) {
+    GemmParams p = gemm_base(M, L.n, L.k, A, lda, L.w, L.wtc, L.wtc_scale, out, ldc);
+    p.bias = L.b;
+    p.relu = relu ? 1 : 0;
+    p.residual = residual; p.ldr = ldr;
+    p.ln_gamma = ln_g; p.ln_beta = ln_b;
+    return run_gemm(r, p, ln_scratch);
+}
+
+int run_conv(const Run& r, const DevConv& c, int n_img, const float* in, int H, int W, float* out, bool relu,
+             const float* residual, bool stem_nchw = false) {
+    const int OH = (H + 2 * c.pad - c.kh) / c.stride + 1;
+    const int OW = (W + 2 * c.pad - c.kw) / c.stride + 1;
+    GemmParams p = gemm_base(n_img * OH * OW, c.cout, c.kh * c.kw * c.cin, in, c.cin, c.w, c.wtc, c.wtc_scale, out, c.cout);
+    if (stem_nchw) {
+        p.a_mode = A_STEM_NCHW;
+    } else if (c.kh == 1 && c.kw == 1 && c.stride == 1) {
+        p.a_mode = A_ROWMAJOR;          // NHWC 1x1 convolution is a plain GEMM over pixels
+    } else {
+        p.a_mode = A_CONV_NHWC;
+    }
+    p.H = H; p.W = W; p.C = c.cin; p.OH = OH; p.OW = OW;
+    p.KH = c.kh; p.KW = c.kw; p.stride = c.stride; p.pad = c.pad;
+    p.bias = c.b;
+    p.relu = relu ? 1 : 0;
+    p.residual = residual; p.ldr = c.cout;
+    return run_gemm(r, p, nullptr);
+}
+
+int run_attention(const Run& r, const AttnParams& p) {
+    r.m->launches++;
+    if (r.m->gemm_path == 0) return launch_attention_tc(p, r.s);
+    return launch_attention_simt(p, r.s);
+}
+
+// ----------------------------------------------------------------------------------------------
+// workspace
+// ----------------------------------------------------------------------------------------------
+constexpr size_t kStemElems = 128 * 128 * 64;      // per image
+constexpr size_t kBigElems = 64 * 64 * 256;        // largest block input / output per image
+constexpr size_t kT1Elems = 64 * 64 * 128;         // largest conv1 output per image (layer2.0)
+constexpr size_t kT2Elems = 64 * 64 * 64;          // largest conv2 output per image (layer1)
+
+size_t encode_ws_floats(int B) {
+    const size_t img = 2 * (size_t)B;
+    const size_t tok = (size_t)B * kTokens;
+    return img * (kStemElems + 3 * kBigElems + kT1Elems + kT2Elems) + tok * (kDModel * 5 + 3 * kDModel + kFF);
+}
+size_t decode_ws_floats(int rows) {
+    return (size_t)rows * (kDModel * 8 + kQpCols + kFF);
+}
+
+int ws_alloc(float** p, size_t elems) {
+    COTR_CHECK_CUDA(cudaMalloc((void**)p, elems * sizeof(float)));
+    return 0;
+}
+void ws_free(float** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+int ensure_encode_ws(cotr_model* m, int B) {
+    Workspace& w = m->ws;
+    if (B <= w.cap_pairs) return 0;
+    COTR_CHECK_CUDA(cudaDeviceSynchronize());
+    float** bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qkv, &w.ao, &w.ffh, &w.tmp};
+    for (float** b : bufs) ws_free(b);
+    const size_t img = 2 * (size_t)B, tok = (size_t)B * kTokens;
+    if (ws_alloc(&w.stem, img * kStemElems) || ws_alloc(&w.bx, img * kBigElems) || ws_alloc(&w.by, img * kBigElems) ||
+        ws_alloc(&w.bds, img * kBigElems) || ws_alloc(&w.bt1, img * kT1Elems) || ws_alloc(&w.bt2, img * kT2Elems) ||
+        ws_alloc(&w.src, tok * kDModel) || ws_alloc(&w.xa, tok * kDModel) || ws_alloc(&w.xb, tok * kDModel) ||
+        ws_alloc(&w.qkv, tok * 3 * kDModel) || ws_alloc(&w.ao, tok * kDModel) || ws_alloc(&w.ffh, tok * kFF) ||
+        ws_alloc(&w.tmp, tok * kDModel))
+        return 1;
+    w.cap_pairs = B;
+    return 0;
+}
+
+int ensure_decode_ws(cotr_model* m, int rows) {
+    Workspace& w = m->ws;
+    if (rows <= w.cap_rows) return 0;
+    COTR_CHECK_CUDA(cudaDeviceSynchronize());
+    float** bufs[] = {&w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dtmp, &w.dh, &w.hs, &w.hd1, &w.hd2};
+    for (float** b : bufs) ws_free(b);
+    const size_t R = rows;
+    if (ws_alloc(&w.qpos, R * kDModel) || ws_alloc(&w.qp, R * kQpCols) || ws_alloc(&w.t, R * kDModel) ||
+        ws_alloc(&w.qb, R * kDModel) || ws_alloc(&w.dao, R * kDModel) || ws_alloc(&w.dtmp, R * kDModel) ||
+        ws_alloc(&w.dh, R * kFF) || ws_alloc(&w.hs, R * kDModel) || ws_alloc(&w.hd1, R * kDModel) ||
+        ws_alloc(&w.hd2, R * kDModel))
+        return 1;
+    w.cap_rows = rows;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// forward schedule
+// ----------------------------------------------------------------------------------------------
+int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaStream_t s) {
+    COTR_CHECK(B >= 1, "cotr_encode_context: B must be >= 1 (got %d)", B);
+    COTR_CHECK(ctx && ctx->model == m, "cotr_encode_context: context does not belong to this model");
+    COTR_CHECK(B <= ctx->max_pairs, "cotr_encode_context: B = %d exceeds the context capacity %d", B, ctx->max_pairs);
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    if (ensure_encode_ws(m, B)) return 1;
+    Workspace& w = m->ws;
+    Run r{m, s};
+    const int n_img = 2 * B;
+
+    // backbone.py:81-82: the two 256x256 halves go through the ResNet body as independent images.
+    // Stem: conv 7x7/2 (+FrozenBN folded) + ReLU, then MaxPool 3x3/2  (torchvision resnet.py _forward_impl).
+    if (run_conv(r, m->stem, n_img, img, 256, 256, w.stem, true, nullptr, /*stem_nchw=*/true)) return 1;
+    m->launches++;
+    if (launch_maxpool_3x3s2_nhwc(w.stem, w.bx, n_img, 128, 128, 64, s)) return 1;
+
+    float* x = w.bx;
+    float* y = w.by;
+    int H = 64, W = 64;
+    for (const Block& b : m->blocks) {
+        // torchvision Bottleneck (v1.5): 1x1 -> 3x3(stride) -> 1x1, + identity | downsample, ReLU
+        if (run_conv(r, b.c1, n_img, x, H, W, w.bt1, true, nullptr)) return 1;
+        if (run_conv(r, b.c2, n_img, w.bt1, H, W, w.bt2, true, nullptr)) return 1;
+        const int OH = H / b.c2.stride, OW = W / b.c2.stride;
+        const float* identity = x;
+        if (b.has_ds) {
+            if (run_conv(r, b.ds, n_img, x, H, W, w.bds, false, nullptr)) return 1;
+            identity = w.bds;
+        }
+        if (run_conv(r, b.c3, n_img, w.bt2, OH, OW, y, true, identity)) return 1;
+        float* t = x; x = y; y = t;
+        H = OH; W = OW;
+    }
+    m->last_feat = x;   // (2B,16,16,1024) NHWC
+
+    // cotr_model.py:37 input_proj (1x1 conv 1024 -> 256) fused with the left|right concat (backbone.py:85)
+    // and the flatten to token-major (transformer.py:50): row = pair*512 + i*32 + j.
+    const int T = B * kTokens;
+    {
+        GemmParams p = gemm_base(T, kDModel, 1024, x, 1024, m->proj.w, m->proj.wtc, m->proj.wtc_scale, w.src, kDModel);
+        p.a_mode = A_TOKENS;
+        p.bias = m->proj.b;
+        if (run_gemm(r, p, nullptr)) return 1;
+    }
+
+    // transformer.py:143-159 x6 (post-LN).  q = k = x + pos is folded into the constant add_qkv matrix.
+    const float* xin = w.src;      // layer input; norm1 output goes to xa, norm2 output (next input) to xb
+    for (int l = 0; l < kEncLayers; ++l) {
+        const EncLayer& e = m->enc[l];
+        {
+            GemmParams p = gemm_base(T, 3 * kDModel, kDModel, xin, kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, w.qkv, 3 * kDModel);
+            p.addmat = e.add_qkv; p.add_period = kTokens; p.ld_add = 3 * kDModel;
+            if (run_gemm(r, p, nullptr)) return 1;
+        }
+        AttnParams a;
+        a.q = w.qkv; a.ldq = 3 * kDModel;
+        a.k = w.qkv + kDModel; a.ldk = 3 * kDModel;
+        a.v = w.qkv + 2 * kDModel; a.ldv = 3 * kDModel;
+        a.out = w.ao; a.ldo = kDModel;
+        a.nq = kTokens; a.npairs = B; a.pair0 = 0;
+        if (run_attention(r, a)) return 1;
+        float* x1 = w.xa;
+        float* x2 = w.xb;
+        // x1 = LN1(x + out_proj(attn))
+        if (run_linear(r, e.o, T, w.ao, kDModel, x1, kDModel, false, xin, kDModel, e.ln1_g, e.ln1_b, w.tmp)) return 1;
+        // x2 = LN2(x1 + W2 relu(W1 x1 + b1) + b2)
+        if (run_linear(r, e.l1, T, x1, kDModel, w.ffh, kFF, true)) return 1;
+        if (run_linear(r, e.l2, T, w.ffh, kFF, x2, kDModel, false, x1, kDModel, e.ln2_g, e.ln2_b, w.tmp)) return 1;
+        xin = x2;
+    }
+    m->last_mem = xin;
+
+    // transformer.py:192-195: K_l = (mem + pos) Wk_l^T + bk_l, V_l = mem Wv_l^T + bv_l for all 6 decoder layers at once.
+    {
+        GemmParams p = gemm_base(T, kKvCols, kDModel, xin, kDModel, m->kv_all.w, m->kv_all.wtc, m->kv_all.wtc_scale, ctx->kv, kKvCols);
+        p.addmat = m->add_kv; p.add_period = kTokens; p.ld_add = kKvCols;
+        if (run_gemm(r, p, nullptr)) return 1;
+    }
+    ctx->pairs = B;
+    m->last_pairs = B;
+    return 0;
+}
+
+int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, float* pred, int pair0, int npairs,
+                 int nq, cudaStream_t s) {
+    Workspace& w = m->ws;
+    Run r{m, s};
+    const int R = npairs * nq;
+    // cotr_model.py:34-35 query_proj (lin_sine, depth 64)
+    m->launches++;
+    if (launch_query_encode(queries, w.qpos, R, s)) return 1;
+    // q-side of transformer.py:192: ((t + qpos) Wq^T + bq) s  =  t (s Wq)^T + [qpos (s Wq)^T + s bq]; the bracket for
+    // all 6 layers is one GEMM.
+    if (run_linear(r, m->qpos_all, R, w.qpos, kDModel, w.qp, kQpCols, false)) return 1;
+
+    for (int l = 0; l < kDecLayers; ++l) {
+        const DecLayer& d = m->dec[l];
+        const float* q = w.qp;      // layer 0: tgt = 0 (transformer.py:54), so q is the qpos projection alone
+        int ldq = kQpCols;
+        if (l > 0) {
+            if (run_linear(r, d.q, R, w.t, kDModel, w.qb, kDModel, false, w.qp + l * kDModel, kQpCols)) return 1;
+            q = w.qb; ldq = kDModel;
+        }
+        AttnParams a;
+        a.q = q; a.ldq = ldq;
+        a.k = ctx->kv + (size_t)l * 2 * kDModel; a.ldk = kKvCols;
+        a.v = ctx->kv + (size_t)l * 2 * kDModel + kDModel; a.ldv = kKvCols;
+        a.out = w.dao; a.ldo = kDModel;
+        a.nq = nq; a.npairs = npairs; a.pair0 = pair0;
+        if (run_attention(r, a)) return 1;
+        // transformer.py:196-197: t = norm2(t + out_proj(attn))
+        if (run_linear(r, d.o, R, w.dao, kDModel, w.t, kDModel, false, l > 0 ? w.t : nullptr, kDModel, d.ln2_g, d.ln2_b, w.dtmp)) return 1;
+        // transformer.py:198-200: t = norm3(t + linear2(relu(linear1(t))))
+        if (run_linear(r, d.l1, R, w.t, kDModel, w.dh, kFF, true)) return 1;
+        if (run_linear(r, d.l2, R, w.dh, kFF, w.t, kDModel, false, w.t, kDModel, d.ln3_g, d.ln3_b, w.dtmp)) return 1;
+    }
+    // transformer.py:110-111 decoder.norm on the last level; cotr_model.py:38-39 corr_embed on that level only.
+    m->launches++;
+    if (launch_layernorm(w.t, nullptr, m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
+    if (run_linear(r, m->head[0], R, w.hs, kDModel, w.hd1, kDModel, true)) return 1;
+    if (run_linear(r, m->head[1], R, w.hd1, kDModel, w.hd2, kDModel, true)) return 1;
+    if (run_linear(r, m->head[2], R, w.hd2, kDModel, pred, 2, false)) return 1;
+    return 0;
+}
+
+int decode_impl(cotr_model* m, const cotr_context* ctx, const float* queries, int B, int Q, float* pred, cudaStream_t s) {
+    COTR_CHECK(ctx && ctx->model == m, "cotr_decode: context does not belong to this model");
+    COTR_CHECK(B >= 1 && B == ctx->pairs, "cotr_decode: B = %d but the context holds %d pairs", B, ctx ? ctx->pairs : -1);
+    COTR_CHECK(Q >= 0, "cotr_decode: negative Q");
+    if (Q == 0) return 0;
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    const long long total = (long long)B * Q;
+    const int cap = (int)(total < kDecodeChunkRows ? total : kDecodeChunkRows);
+    if (ensure_decode_ws(m, cap)) return 1;
+    if (Q <= kDecodeChunkRows) {
+        const int pairs_per = kDecodeChunkRows / Q;
+        for (int b0 = 0; b0 < B; b0 += pairs_per) {
+            const int nb = (B - b0 < pairs_per) ? B - b0 : pairs_per;
+            if (decode_chunk(m, ctx, queries + (size_t)b0 * Q * 2, pred + (size_t)b0 * Q * 2, b0, nb, Q, s)) return 1;
+        }
+    } else {
+        for (int b = 0; b < B; ++b)
+            for (int q0 = 0; q0 < Q; q0 += kDecodeChunkRows) {
+                const int nq = (Q - q0 < kDecodeChunkRows) ? Q - q0 : kDecodeChunkRows;
+                const size_t off = ((size_t)b * Q + q0) * 2;
+                if (decode_chunk(m, ctx, queries + off, pred + off, b, 1, nq, s)) return 1;
+            }
+    }
+    m->last_rows = (total <= kDecodeChunkRows) ? (int)total : 0;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// model construction
+// ----------------------------------------------------------------------------------------------
+int build_model(cotr_model* m, const TensorMap& tm) {
+    const std::string body = "backbone.0.body";
+    if (make_conv(m, tm, body + ".conv1", body + ".bn1", 64, 3, 7, 7, 2, 3, &m->stem)) return 1;
+    struct LayerCfg { const char* name; int n, planes, stride; };
+    const LayerCfg layers[3] = {{"layer1", 3, 64, 1}, {"layer2", 4, 128, 2}, {"layer3", 6, 256, 2}};
+    int inplanes = 64;
+    for (const LayerCfg& L : layers) {
+        for (int i = 0; i < L.n; ++i) {
+            const std::string p = body + "." + L.name + "." + std::to_string(i);
+            Block b;
+            const int stride = (i == 0) ? L.stride : 1;
+            if (make_conv(m, tm, p + ".conv1", p + ".bn1", L.planes, inplanes, 1, 1, 1, 0, &b.c1)) return 1;
+            if (make_conv(m, tm, p + ".conv2", p + ".bn2", L.planes, L.planes, 3, 3, stride, 1, &b.c2)) return 1;
+            if (make_conv(m, tm, p + ".conv3", p + ".bn3", L.planes * 4, L.planes, 1, 1, 1, 0, &b.c3)) return 1;
+            b.has_ds = (i == 0);
+            if (b.has_ds && make_conv(m, tm, p + ".downsample.0", p + ".downsample.1", L.planes * 4, inplanes, 1, 1, stride, 0, &b.ds)) return 1;
+            m->blocks.push_back(b);
+            inplanes = L.planes * 4;
+        }
+    }
+    {
+        const cotr_tensor* w = tm.get("input_proj.weight", {kDModel, 1024, 1, 1});
+        const cotr_tensor* b = tm.get("input_proj.bias", {kDModel});
+        if (!w || !b) return 1;
+        std::vector<float> bv = to_vec(b, kDModel);
+        if (make_linear(m, to_vec(w, (size_t)kDModel * 1024), &bv, kDModel, 1024, &m->proj)) return 1;
+    }
+    if (upload(m, grid_position_table(), &m->pos)) return 1;
+
+    const float qscale = 1.0f / std::sqrt((float)kHeadDim);   // F.multi_head_attention_forward: q * head_dim^-0.5
+    const size_t DD = (size_t)kDModel * kDModel;
+
+    auto linear_from = [&](const std::string& prefix, int N, int K, DevLinear* out) -> int {
+        const cotr_tensor* w = tm.get(prefix + ".weight", {N, K});
+        const cotr_tensor* b = tm.get(prefix + ".bias", {N});
+        if (!w || !b) return 1;
+        std::vector<float> bv = to_vec(b, N);
+        return make_linear(m, to_vec(w, (size_t)N * K), &bv, N, K, out);
+    };
+
+    // temporary device buffers for the constant position-bias matrices, produced with the fp32 SIMT GEMM
+    struct PosBiasJob { std::vector<float> w_masked; std::vector<float> bias; int N; float** dst; };
+    std::vector<PosBiasJob> jobs;
+
+    for (int l = 0; l < kEncLayers; ++l) {
+        const std::string p = "transformer.encoder.layers." + std::to_string(l);
+        EncLayer& e = m->enc[l];
+        const cotr_tensor* w = tm.get(p + ".self_attn.in_proj_weight", {3 * kDModel, kDModel});
+        const cotr_tensor* b = tm.get(p + ".self_attn.in_proj_bias", {3 * kDModel});
+        if (!w || !b) return 1;
+        std::vector<float> wv = to_vec(w, 3 * DD), bv = to_vec(b, 3 * kDModel);
+        for (size_t i = 0; i < DD; ++i) wv[i] *= qscale;
+        for (int i = 0; i < kDModel; ++i) bv[i] *= qscale;
+        if (make_linear(m, wv, nullptr, 3 * kDModel, kDModel, &e.qkv)) return 1;
+        std::vector<float> wm = wv;                               // value rows see x only, not x + pos
+        std::fill(wm.begin() + 2 * DD, wm.end(), 0.f);
+        jobs.push_back({wm, bv, 3 * kDModel, &e.add_qkv});
+        if (linear_from(p + ".self_attn.out_proj", kDModel, kDModel, &e.o)) return 1;
+        if (linear_from(p + ".linear1", kFF, kDModel, &e.l1)) return 1;
+        if (linear_from(p + ".linear2", kDModel, kFF, &e.l2)) return 1;
+        if (upload_vec(m, tm, p + ".norm1.weight", kDModel, &e.ln1_g) || upload_vec(m, tm, p + ".norm1.bias", kDModel, &e.ln1_b) ||
+            upload_vec(m, tm, p + ".norm2.weight", kDModel, &e.ln2_g) || upload_vec(m, tm, p + ".norm2.bias", kDModel, &e.ln2_b))
+            return 1;
+    }
+
+    std::vector<float> kv_w((size_t)kKvCols * kDModel), kv_wm((size_t)kKvCols * kDModel, 0.f), kv_b(kKvCols);
+    std::vector<float> qp_w((size_t)kQpCols * kDModel), qp_b(kQpCols);
+    for (int l = 0; l < kDecLayers; ++l) {
+        const std::string p = "transformer.decoder.layers." + std::to_string(l);
+        DecLayer& d = m->dec[l];
+        const cotr_tensor* w = tm.get(p + ".multihead_attn.in_proj_weight", {3 * kDModel, kDModel});
+        const cotr_tensor* b = tm.get(p + ".multihead_attn.in_proj_bias", {3 * kDModel});
+        if (!w || !b) return 1;
+        std::vector<float> wq = to_vec(w, DD);
+        for (float& v : wq) v *= qscale;
+        if (make_linear(m, wq, nullptr, kDModel, kDModel, &d.q)) return 1;
+        memcpy(qp_w.data() + (size_t)l * DD, wq.data(), DD * sizeof(float));
+        for (int i = 0; i < kDModel; ++i) qp_b[l * kDModel + i] = b->data[i] * qscale;
+        // K rows then V rows of layer l
+        memcpy(kv_w.data() + (size_t)l * 2 * DD, w->data + DD, 2 * DD * sizeof(float));
+        memcpy(kv_wm.data() + (size_t)l * 2 * DD, w->data + DD, DD * sizeof(float));   // only K sees pos
+        memcpy(kv_b.data() + (size_t)l * 2 * kDModel, b->data + kDModel, 2 * kDModel * sizeof(float));
+        if (linear_from(p + ".multihead_attn.out_proj", kDModel, kDModel, &d.o)) return 1;
+        if (linear_from(p + ".linear1", kFF, kDModel, &d.l1)) return 1;
+        if (linear_from(p + ".linear2", kDModel, kFF, &d.l2)) return 1;
+        if (upload_vec(m, tm, p + ".norm2.weight", kDModel, &d.ln2_g) || upload_vec(m, tm, p + ".norm2.bias", kDModel, &d.ln2_b) ||
+            upload_vec(m, tm, p + ".norm3.weight", kDModel, &d.ln3_g) || upload_vec(m, tm, p + ".norm3.bias", kDModel, &d.ln3_b))
+            return 1;
+        // decoder.layers.N.norm1.* exists in the checkpoint but transformer.py:185-201 never uses it.
+    }
+    if (make_linear(m, kv_w, nullptr, kKvCols, kDModel, &m->kv_all)) return 1;
+    jobs.push_back({kv_wm, kv_b, kKvCols, &m->add_kv});
+    if (make_linear(m, qp_w, &qp_b, kQpCols, kDModel, &m->qpos_all)) return 1;
+    if (upload_vec(m, tm, "transformer.decoder.norm.weight", kDModel, &m->dec_norm_g) ||
+        upload_vec(m, tm, "transformer.decoder.norm.bias", kDModel, &m->dec_norm_b))
+        return 1;
+    if (linear_from("corr_embed.layers.0", kDModel, kDModel, &m->head[0])) return 1;
+    if (linear_from("corr_embed.layers.1", kDModel, kDModel, &m->head[1])) return 1;
+    if (linear_from("corr_embed.layers.2", 2, kDModel, &m->head[2])) return 1;
+
+    // add matrices: pos [512,256] x Wmasked^T + bias  (fp32 SIMT GEMM, once per model)
+    for (PosBiasJob& j : jobs) {
+        float *wd = nullptr, *bd = nullptr;
+        COTR_CHECK_CUDA(cudaMalloc((void**)&wd, j.w_masked.size() * sizeof(float)));
+        COTR_CHECK_CUDA(cudaMalloc((void**)&bd, j.bias.size() * sizeof(float)));
+        COTR_CHECK_CUDA(cudaMemcpy(wd, j.w_masked.data(), j.w_masked.size() * sizeof(float), cudaMemcpyHostToDevice));
+        COTR_CHECK_CUDA(cudaMemcpy(bd, j.bias.data(), j.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (dev_alloc(m, (void**)j.dst, (size_t)kTokens * j.N * sizeof(float))) return 1;
+        GemmParams p = gemm_base(kTokens, j.N, kDModel, m->pos, kDModel, wd, nullptr, 1.f, *j.dst, j.N);
+        p.bias = bd;
+        if (launch_gemm_simt(p, 0)) return 1;
+        COTR_CHECK_CUDA(cudaDeviceSynchronize());
+        cudaFree(wd);
+        cudaFree(bd);
+    }
+    return 0;
+}
+
+}  // namespace
+}  // namespace cotr
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace cotr;
+
+extern "C" {
+
+const char* cotr_last_error(void) { return g_error; }
+const char* cotr_version(void) { return "cotr_b200 0.1 (sm_100a)"; }
+
+int cotr_create(int device, const cotr_tensor* tensors, int n_tensors, cotr_model** out) {
+    COTR_CHECK(out != nullptr && tensors != nullptr && n_tensors > 0, "cotr_create: bad arguments");
+    *out = nullptr;
+    int n_dev = 0;
+    COTR_CHECK_CUDA(cudaGetDeviceCount(&n_dev));
+    COTR_CHECK(device >= 0 && device < n_dev, "cotr_create: CUDA device %d not available (%d visible)", device, n_dev);
+    COTR_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    COTR_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    COTR_CHECK(prop.major == 10, "cotr_create: this library is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    TensorMap tm;
+    for (int i = 0; i < n_tensors; ++i) {
+        COTR_CHECK(tensors[i].name != nullptr, "cotr_create: tensor %d has no name", i);
+        tm.m[tensors[i].name] = &tensors[i];
+    }
+    cotr_model* m = new cotr_model();
+    m->device = device;
+    if (build_model(m, tm) || cotr_context_create(m, 1, &m->own_ctx) ||
+        cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        if (g_error[0] == 0) set_error("cotr_create: stream creation failed");
+        cotr_destroy(m);
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
+void cotr_destroy(cotr_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    if (m->own_ctx) cotr_context_destroy(m->own_ctx);
+    for (void* p : m->allocs) cudaFree(p);
+    Workspace& w = m->ws;
+    float** bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qkv, &w.ao, &w.ffh, &w.tmp,
+                      &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dtmp, &w.dh, &w.hs, &w.hd1, &w.hd2,
+                      &w.img_stage, &w.q_stage, &w.pred_stage};
+    for (float** b : bufs) ws_free(b);
+    if (m->host_stream) cudaStreamDestroy(m->host_stream);
+    delete m;
+}
+
+int cotr_context_create(cotr_model* m, int max_pairs, cotr_context** out) {
+    COTR_CHECK(m && out && max_pairs >= 1, "cotr_context_create: bad arguments");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    cotr_context* c = new cotr_context();
+    c->model = m;
+    c->max_pairs = max_pairs;
+    if (cudaMalloc((void**)&c->kv, (size_t)max_pairs * kTokens * kKvCols * sizeof(float)) != cudaSuccess) {
+        set_error("cotr_context_create: out of device memory for %d pairs", max_pairs);
+        delete c;
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+void cotr_context_destroy(cotr_context* c) {
+    if (!c) return;
+    if (c->kv) cudaFree(c->kv);
+    delete c;
+}
+
+int cotr_encode_context(cotr_model* m, const float* img_dev, int B, cotr_context* ctx, void* cuda_stream) {
+    COTR_CHECK(m && img_dev, "cotr_encode_context: null argument");
+    m->launches = 0;
+    return encode_impl(m, img_dev, B, ctx, (cudaStream_t)cuda_stream);
+}
+
+int cotr_decode(cotr_model* m, const cotr_context* ctx, const float* queries_dev, int B, int Q, float* pred_dev, void* cuda_stream) {
+    COTR_CHECK(m && (Q == 0 || (queries_dev && pred_dev)), "cotr_decode: null argument");
+    m->launches = 0;
+    return decode_impl(m, ctx, queries_dev, B, Q, pred_dev, (cudaStream_t)cuda_stream);
+}
+
+int cotr_forward(cotr_model* m, const float* img_dev, const float* queries_dev, int B, int Q, float* pred_dev, void* cuda_stream) {
+    COTR_CHECK(m && img_dev && (Q == 0 || (queries_dev && pred_dev)), "cotr_forward: null argument");
+    COTR_CHECK(B >= 1, "cotr_forward: B must be >= 1");
+    if (m->own_ctx->max_pairs < B) {
+        COTR_CHECK_CUDA(cudaDeviceSynchronize());
+        cotr_context_destroy(m->own_ctx);
+        m->own_ctx = nullptr;
+        if (cotr_context_create(m, B, &m->own_ctx)) return 1;
+    }
+    m->launches = 0;
+    if (encode_impl(m, img_dev, B, m->own_ctx, (cudaStream_t)cuda_stream)) return 1;
+    return decode_impl(m, m->own_ctx, queries_dev, B, Q, pred_dev, (cudaStream_t)cuda_stream);
+}
+
+int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries_host, int B, int Q, float* pred_host) {
+    COTR_CHECK(m && img_host && (Q == 0 || (queries_host && pred_host)), "cotr_forward_host: null argument");
+    COTR_CHECK(B >= 1, "cotr_forward_host: B must be >= 1");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    Workspace& w = m->ws;
+    const size_t img_elems = (size_t)B * 3 * COTR_CANVAS_H * COTR_CANVAS_W;
+    const size_t q_elems = (size_t)B * Q * 2;
+    if (img_elems > w.img_stage_elems) {
+        COTR_CHECK_CUDA(cudaDeviceSynchronize());
+        ws_free(&w.img_stage);
+        if (ws_alloc(&w.img_stage, img_elems)) return 1;
+        w.img_stage_elems = img_elems;
+    }
+    if (q_elems > w.q_stage_elems) {
+        COTR_CHECK_CUDA(cudaDeviceSynchronize());
+        ws_free(&w.q_stage); ws_free(&w.pred_stage);
+        if (ws_alloc(&w.q_stage, q_elems) || ws_alloc(&w.pred_stage, q_elems)) return 1;
+        w.q_stage_elems = q_elems;
+    }
+    cudaStream_t s = m->host_stream;
+    COTR_CHECK_CUDA(cudaMemcpyAsync(w.img_stage, img_host, img_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (q_elems) COTR_CHECK_CUDA(cudaMemcpyAsync(w.q_stage, queries_host, q_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (cotr_forward(m, w.img_stage, w.q_stage, B, Q, w.pred_stage, s)) return 1;
+    if (q_elems) COTR_CHECK_CUDA(cudaMemcpyAsync(pred_host, w.pred_stage, q_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    COTR_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+size_t cotr_workspace_bytes(int B, int Q) {
+    if (B < 1 || Q < 0) return 0;
+    const long long total = (long long)B * Q;
+    const int rows = (int)(total < kDecodeChunkRows ? total : kDecodeChunkRows);
+    return (encode_ws_floats(B) + decode_ws_floats(rows)) * sizeof(float);
+}
+
+int cotr_last_launch_count(const cotr_model* m) { return m ? m->launches : -1; }
+
+int64_t cotr_debug_read(cotr_model* m, const char* name, float* out_host, int64_t max_elems) {
+    if (!m || !name || !out_host) return -1;
+    cudaSetDevice(m->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    const float* src = nullptr;
+    int64_t n = 0;
+    const std::string s(name);
+    if (s == "feat") { src = m->last_feat; n = (int64_t)m->last_pairs * 2 * 16 * 16 * 1024; }
+    else if (s == "src") { src = m->ws.src; n = (int64_t)m->last_pairs * kTokens * kDModel; }
+    else if (s == "mem") { src = m->last_mem; n = (int64_t)m->last_pairs * kTokens * kDModel; }
+    else if (s == "hs") { src = m->ws.hs; n = (int64_t)m->last_rows * kDModel; }
+    else if (s == "pos") { src = m->pos; n = (int64_t)kTokens * kDModel; }
+    if (!src || n <= 0 || n > max_elems) return -1;
+    if (cudaMemcpy(out_host, src, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
+}
+
+int cotr_set_gemm_path(cotr_model* m, int path) {
+    COTR_CHECK(m && (path == 0 || path == 1), "cotr_set_gemm_path: path must be 0 (tcgen05) or 1 (fp32 SIMT)");
+    m->gemm_path = path;
+    return 0;
+}
+
+void cotr_debug_set_variant(int variant) { g_tc_variant = variant; }
+
+int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float* w_host, const float* bias_dev,
+                   const float* addmat_dev, const float* residual_dev, const float* ln_gamma_dev,
+                   const float* ln_beta_dev, float* out_dev) {
+    COTR_CHECK(d && A_dev && w_host && out_dev, "cotr_test_gemm: null argument");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = d->M; p.N = d->N; p.K = d->K;
+    p.A = A_dev; p.a_mode = d->a_mode; p.lda = d->lda;
+    p.H = d->H; p.W = d->W; p.C = d->C; p.OH = d->OH; p.OW = d->OW;
+    p.KH = d->KH; p.KW = d->KW; p.stride = d->stride; p.pad = d->pad;
+    p.bias = bias_dev; p.addmat = addmat_dev; p.add_period = d->add_period > 0 ? d->add_period : 1; p.ld_add = d->ld_add;
+    p.residual = residual_dev; p.ldr = d->ldr; p.relu = d->relu;
+    p.ln_gamma = ln_gamma_dev; p.ln_beta = ln_beta_dev;
+    p.out = out_dev; p.ldc = d->ldc;
+    float* wd = nullptr;
+    void* wtc = nullptr;
+    const size_t wn = (size_t)d->N * d->K;
+    COTR_CHECK_CUDA(cudaMalloc((void**)&wd, wn * sizeof(float)));
+    COTR_CHECK_CUDA(cudaMemcpy(wd, w_host, wn * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t tcb = tc_weight_bytes(d->N, d->K);
+    std::vector<uint8_t> img(tcb);
+    p.acc_scale = tc_pack_weight(w_host, d->N, d->K, img.data());
+    COTR_CHECK_CUDA(cudaMalloc(&wtc, tcb));
+    COTR_CHECK_CUDA(cudaMemcpy(wtc, img.data(), tcb, cudaMemcpyHostToDevice));
+    p.Wt = wd; p.Wtc = wtc;
+    int rc;
+    if (d->path == 0) {
+        rc = launch_gemm_tc(p, 0);
+    } else {
+        const float* g = p.ln_gamma; const float* b = p.ln_beta;
+        p.ln_gamma = nullptr; p.ln_beta = nullptr;
+        rc = launch_gemm_simt(p, 0);
+        if (!rc && g) rc = launch_layernorm(p.out, nullptr, g, b, p.out, p.M, 0);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(wd);
+    cudaFree(wtc);
+    if (rc) return rc;
+    COTR_CHECK(e == cudaSuccess, "cotr_test_gemm: kernel failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const float* v_dev, float* out_dev,
+                        int nq, int npairs) {
+    COTR_CHECK(q_dev && k_dev && v_dev && out_dev, "cotr_test_attention: null argument");
+    AttnParams a;
+    a.q = q_dev; a.ldq = kDModel; a.k = k_dev; a.ldk = kDModel; a.v = v_dev; a.ldv = kDModel;
+    a.out = out_dev; a.ldo = kDModel; a.nq = nq; a.npairs = npairs; a.pair0 = 0;
+    const int rc = path == 0 ? launch_attention_tc(a, 0) : launch_attention_simt(a, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc) return rc;
+    COTR_CHECK(e == cudaSuccess, "cotr_test_attention: kernel failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,332 @@
+"""Host scheduler of the recursive zoom-in (reference: COTR/inference/sparse_engine.py).
+
+`SparseEngine` runs one query per network context (sparse_engine.py:17-264); `FasterSparseEngine` lets nearby
+tasks share the context of a "pilot" task (:267-427).  Task state, RNG call order (`np.random.choice` with
+replacement in gen_tasks, `np.random.permutation` per grouped batch), truncation rules and the acceptance /
+border / cycle-consistency filters follow the reference so that, driven by the same model, both produce the same
+correspondences - including the reference's quirk that the faster engine strands tasks which were never grouped at
+an earlier zoom level.
+"""
+import numpy as np
+import PIL.Image
+import torch
+
+from .inference_helper import THRESHOLD_SPARSE, THRESHOLD_AREA, cotr_flow, cotr_corr_base
+from .refinement_task import RefinementTask
+from ..utils import utils
+
+
+def stretch_to_square_np(img):
+    """Resize to max(h,w) x max(h,w) with Pillow bilinear (reference: COTR/cameras/capture.py:123-125)."""
+    size = max(*img.shape[:2])
+    return np.array(PIL.Image.fromarray(img).resize((size, size), resample=PIL.Image.BILINEAR))
+
+
+def _is_open(task, zoom=None):
+    if task.status != 'unfinished' or task.submitted:
+        return False
+    return zoom is None or task.cur_zoom == zoom
+
+
+class SparseEngine():
+    def __init__(self, model, batch_size, mode='stretching'):
+        assert mode in ['stretching', 'tile']
+        self.model = model
+        self.batch_size = batch_size
+        self.total_tasks = 0
+        self.mode = mode
+
+    # ---- batching ------------------------------------------------------------------------------------------
+    def form_batch(self, tasks, zoom=None):
+        """First `batch_size` open tasks (optionally at one zoom level) -> stacked canvases and queries (:25-45)."""
+        task_ref, imgs, queries = [], [], []
+        for t in tasks:
+            if not _is_open(t, zoom):
+                continue
+            img, query = t.get_task()
+            task_ref.append(t)
+            imgs.append(img)
+            queries.append(query)
+            if len(task_ref) >= self.batch_size:
+                break
+        if not task_ref:
+            return [], [], []
+        return task_ref, torch.stack(imgs), torch.stack(queries)
+
+    def infer_batch(self, img_batch, query_batch):
+        """(n,3,256,512) + (n,1,2) -> (n,2) numpy; NaN raises like the reference (:47-56)."""
+        self.total_tasks += img_batch.shape[0]
+        device = next(self.model.parameters()).device
+        out = self.model(img_batch.to(device), query_batch.to(device))['pred_corrs'].clone().detach()
+        out = out.cpu().numpy()[:, 0, :]
+        if utils.has_nan(out):
+            raise ValueError('NaN in prediction')
+        return out
+
+    def conclude_tasks(self, tasks, return_idx=False, force=False, offset_x_from=0, offset_y_from=0, offset_x_to=0,
+                       offset_y_to=0, img_a_shape=None, img_b_shape=None):
+        """Collect accepted results of finished tasks; drop those on / outside the image borders (:58-84)."""
+        corrs, idx = [], []
+        for t in tasks:
+            if t.status != 'finished':
+                continue
+            out = t.conclude(force)
+            if out is not None:
+                corrs.append(np.array(out))
+                idx.append(t.identifier)
+        corrs = np.array(corrs)
+        idx = np.array(idx)
+        if corrs.shape[0] > 0:
+            corrs -= np.array([offset_x_from, offset_y_from, offset_x_to, offset_y_to])
+            if img_a_shape is not None and img_b_shape is not None and not force:
+                upper = np.concatenate([img_a_shape[::-1], img_b_shape[::-1]])
+                inside = np.all(corrs < upper, axis=1) & np.all(corrs > 0, axis=1)
+                corrs = corrs[inside]
+                idx = idx[inside]
+        if return_idx:
+            return corrs, idx
+        return corrs
+
+    def num_finished_tasks(self, tasks):
+        return sum(1 for t in tasks if t.status == 'finished')
+
+    def num_good_tasks(self, tasks):
+        return sum(1 for t in tasks if t.result == 'good')
+
+    # ---- task generation -----------------------------------------------------------------------------------
+    def gen_tasks_w_known_scale(self, img_a, img_b, queries_a, areas, zoom_ins=[1.0], converge_iters=1, max_corrs=1000):
+        assert self.mode == 'tile'
+        corr_a = cotr_corr_base(self.model, img_a, img_b, queries_a)
+        return [RefinementTask(img_a, img_b, c[:2], c[2:], areas[0], areas[1], converge_iters, zoom_ins) for c in corr_a]
+
+    def _dense_first_guess(self, img_a, img_b):
+        """cotr_flow on the pair (stretched to squares in 'stretching' mode, :114-139)."""
+        needs_stretch = self.mode == 'stretching' and (img_a.shape[0] != img_a.shape[1] or img_b.shape[0] != img_b.shape[1])
+        if self.mode not in ('stretching', 'tile'):
+            raise ValueError(f'unsupported mode: {self.mode}')
+        if not needs_stretch:
+            return cotr_flow(self.model, img_a, img_b)
+        maps = cotr_flow(self.model, stretch_to_square_np(img_a.copy()), stretch_to_square_np(img_b.copy()))
+        shapes = (img_a.shape[:2],) * 3 + (img_b.shape[:2],) * 3
+        return tuple(utils.float_image_resize(m, s) for m, s in zip(maps, shapes))
+
+    def gen_tasks(self, img_a, img_b, zoom_ins=[1.0], converge_iters=1, max_corrs=1000, queries_a=None, force=False, areas=None):
+        if areas is not None:
+            assert queries_a is not None
+            assert force == True
+            assert max_corrs >= queries_a.shape[0]
+            return self.gen_tasks_w_known_scale(img_a, img_b, queries_a, areas, zoom_ins=zoom_ins,
+                                                converge_iters=converge_iters, max_corrs=max_corrs)
+        corr_a, con_a, _, corr_b, con_b, _ = self._dense_first_guess(img_a, img_b)
+        mask_a = con_a < THRESHOLD_SPARSE
+        mask_b = con_b < THRESHOLD_SPARSE
+        area_a = (con_a < THRESHOLD_AREA).sum() / mask_a.size
+        area_b = (con_b < THRESHOLD_AREA).sum() / mask_b.size
+        size_a_xy = img_a.shape[:2][::-1]
+        size_b_xy = img_b.shape[:2][::-1]
+
+        def guess(corr, pos_rc, size_xy):
+            """[-1,1] dense prediction at integer pixel (row, col) -> pixel location in the other image."""
+            return (corr[tuple(pos_rc)].copy() * 0.5 + 0.5) * size_xy
+
+        def new_task(loc_from, loc_to, identifier=None):
+            return RefinementTask(img_a, img_b, loc_from, loc_to, area_a, area_b, converge_iters, zoom_ins, identifier=identifier)
+
+        tasks = []
+        if queries_a is None:
+            # sample (with replacement) confident pixels of both dense maps (:147-166); RNG order: a then b
+            cand_a = np.array(np.where(mask_a)).T
+            cand_a = cand_a[np.random.choice(len(cand_a), min(max_corrs, len(cand_a)))]
+            cand_b = np.array(np.where(mask_b)).T
+            cand_b = cand_b[np.random.choice(len(cand_b), min(max_corrs, len(cand_b)))]
+            for pos in cand_a:
+                tasks.append(new_task(pos[::-1], guess(corr_a, np.floor(pos).astype('int'), size_b_xy)))
+            for pos in cand_b:
+                # b->a samples keep their first guess as the fixed end: from/to are swapped on purpose (:159-166)
+                tasks.append(new_task(guess(corr_b, np.floor(pos).astype('int'), size_a_xy), pos[::-1]))
+            return tasks
+
+        if force:
+            for i, loc_from in enumerate(queries_a):
+                pos = loc_from[::-1]
+                pos = np.array([np.clip(pos[0], 0, corr_a.shape[0] - 1), np.clip(pos[1], 0, corr_a.shape[1] - 1)], dtype=int)
+                tasks.append(new_task(loc_from, guess(corr_a, pos, size_b_xy), identifier=i))
+            return tasks
+
+        def usable(loc_from):
+            pos = loc_from[::-1]
+            if (pos > np.array(img_a.shape[:2]) - 1).any() or (pos < 0).any():
+                return None
+            return np.floor(pos).astype('int')
+
+        for i, loc_from in enumerate(queries_a):          # confident queries first (:176-182)
+            pos = usable(loc_from)
+            if pos is not None and mask_a[tuple(pos)]:
+                tasks.append(new_task(loc_from, guess(corr_a, pos, size_b_xy), identifier=i))
+        if len(tasks) < max_corrs:                        # then top up with unconfident ones (:183-195)
+            extra = max_corrs - len(tasks)
+            added = 0
+            for i, loc_from in enumerate(queries_a):
+                if added >= extra:
+                    break
+                pos = usable(loc_from)
+                if pos is not None and mask_a[tuple(pos)] == False:
+                    tasks.append(new_task(loc_from, guess(corr_a, pos, size_b_xy), identifier=i))
+                    added += 1
+        return tasks
+
+    # ---- drivers -------------------------------------------------------------------------------------------
+    def _single_query_loop(self, tasks, max_corrs, zoom=None):
+        while True:
+            num_g = self.num_good_tasks(tasks)
+            print(f'{num_g} / {max_corrs} | {self.num_finished_tasks(tasks)} / {len(tasks)}')
+            task_ref, img_batch, query_batch = self.form_batch(tasks, zoom)
+            if len(task_ref) == 0 or num_g >= max_corrs:
+                break
+            out = self.infer_batch(img_batch, query_batch)
+            for t, o in zip(task_ref, out):
+                t.step(o)
+
+    def _finish(self, tasks, max_corrs, return_idx, force, return_tasks_only, img_a_shape, img_b_shape):
+        if return_tasks_only:
+            return tasks
+        if return_idx:
+            corrs, idx = self.conclude_tasks(tasks, return_idx=True, force=force, img_a_shape=img_a_shape, img_b_shape=img_b_shape)
+            return corrs[:max_corrs], idx[:max_corrs]
+        return self.conclude_tasks(tasks, force=force, img_a_shape=img_a_shape, img_b_shape=img_b_shape)[:max_corrs]
+
+    def cotr_corr_multiscale(self, img_a, img_b, zoom_ins=[1.0], converge_iters=1, max_corrs=1000, queries_a=None,
+                             return_idx=False, force=False, return_tasks_only=False, areas=None):
+        """Correspondences (<=max_corrs, 4) [x_a, y_a, x_b, y_b] in pixels (:197-233)."""
+        img_a = img_a.copy()
+        img_b = img_b.copy()
+        if queries_a is not None:
+            queries_a = queries_a.copy()
+        tasks = self.gen_tasks(img_a, img_b, zoom_ins, converge_iters, max_corrs, queries_a, force, areas)
+        self._single_query_loop(tasks, max_corrs)
+        return self._finish(tasks, max_corrs, return_idx, force, return_tasks_only, img_a.shape[:2], img_b.shape[:2])
+
+    def cotr_corr_multiscale_with_cycle_consistency(self, img_a, img_b, zoom_ins=[1.0], converge_iters=1, max_corrs=1000,
+                                                    queries_a=None, return_idx=False, return_cycle_error=False):
+        """a->b, then b->a on the a->b answers; keep the max_corrs smallest cycle errors (:235-264)."""
+        EXTRACTION_RATE = 0.3
+        temp_max_corrs = int(max_corrs / EXTRACTION_RATE)
+        if queries_a is not None:
+            temp_max_corrs = min(temp_max_corrs, queries_a.shape[0])
+            queries_a = queries_a.copy()
+        corr_f, idx_f = self.cotr_corr_multiscale(img_a.copy(), img_b.copy(), zoom_ins=zoom_ins, converge_iters=converge_iters,
+                                                  max_corrs=temp_max_corrs, queries_a=queries_a, return_idx=True)
+        assert corr_f.shape[0] > 0
+        corr_b, idx_b = self.cotr_corr_multiscale(img_b.copy(), img_a.copy(), zoom_ins=zoom_ins, converge_iters=converge_iters,
+                                                  max_corrs=corr_f.shape[0], queries_a=corr_f[:, 2:].copy(), return_idx=True)
+        assert corr_b.shape[0] > 0
+        cycle_errors = np.linalg.norm(corr_f[idx_b][:, :2] - corr_b[:, 2:], axis=1)
+        order = np.argsort(cycle_errors)
+        out = [corr_f[idx_b][order][:max_corrs]]
+        if return_idx:
+            out.append(idx_f[idx_b][order][:max_corrs])
+        if return_cycle_error:
+            out.append(cycle_errors[order][:max_corrs])
+        return out[0] if len(out) == 1 else out
+
+
+class FasterSparseEngine(SparseEngine):
+    """Nearby tasks share one network context: faster, slightly less accurate (:267-427)."""
+
+    def __init__(self, model, batch_size, mode='stretching', max_load=256):
+        super().__init__(model, batch_size, mode=mode)
+        self.max_load = max_load
+
+    def infer_batch_grouped(self, img_batch, query_batch):
+        device = next(self.model.parameters()).device
+        return self.model(img_batch.to(device), query_batch.to(device))['pred_corrs'].clone().detach().cpu().numpy()
+
+    def get_tasks_map(self, zoom, tasks):
+        """(n,4) [x_from, y_from, x_to, y_to] of every open task at `zoom` + their indices into `tasks` (:284-293)."""
+        points, ids = [], []
+        for i, t in enumerate(tasks):
+            if _is_open(t, zoom):
+                info = t.peek()
+                points.append(np.concatenate([info['loc_from'], info['loc_to']]))
+                ids.append(i)
+        return np.array(points), np.array(ids)
+
+    def form_squad(self, zoom, pilot, pilot_id, tasks, tasks_map, task_ids, bookkeeping):
+        """The pilot's crops define the context; free tasks whose two end points fall in the central half of both
+        crops ride along (at most max_load of them) (:295-337)."""
+        assert pilot.status == 'unfinished' and pilot.submitted == False and pilot.cur_zoom == zoom
+        SAFE_AREA = 0.5
+        info = pilot.peek()
+
+        def safe_box(p):
+            cx, cy = p.x + p.w / 2, p.y + p.h / 2
+            return cx - p.w / 2 * SAFE_AREA, cx + p.w / 2 * SAFE_AREA, cy - p.h / 2 * SAFE_AREA, cy + p.h / 2 * SAFE_AREA
+
+        f_l, f_r, f_u, f_d = safe_box(info['patch_from'])
+        t_l, t_r, t_u, t_d = safe_box(info['patch_to'])
+        img, query = pilot.get_task()
+        assert pilot.submitted == True
+        members, queries = [pilot], [query]
+        bookkeeping[pilot_id] = False
+        fits = ((tasks_map[:, 0] > f_l) & (tasks_map[:, 0] < f_r) & (tasks_map[:, 1] > f_u) & (tasks_map[:, 1] < f_d) &
+                (tasks_map[:, 2] > t_l) & (tasks_map[:, 2] < t_r) & (tasks_map[:, 3] > t_u) & (tasks_map[:, 3] < t_d))
+        loads = np.where(fits * bookkeeping)[0][: self.max_load]
+        for ti in task_ids[loads]:
+            t = tasks[ti]
+            assert t.status == 'unfinished' and t.submitted == False and t.cur_zoom == zoom
+            _, query = t.get_task_pilot(pilot)
+            members.append(t)
+            queries.append(query)
+        bookkeeping[loads] = False
+        return members, img, torch.stack(queries, axis=1), bookkeeping
+
+    def form_grouped_batch(self, zoom, tasks):
+        """Up to batch_size squads; queries zero-padded to the longest squad (:339-369)."""
+        tasks_map, task_ids = self.get_tasks_map(zoom, tasks)
+        shuffle = np.random.permutation(tasks_map.shape[0])
+        tasks_map = np.take(tasks_map, shuffle, axis=0)
+        task_ids = np.take(task_ids, shuffle, axis=0)
+        bookkeeping = np.ones_like(task_ids).astype(bool)
+        task_ref, imgs, queries = [], [], []
+        for i, ti in enumerate(task_ids):
+            t = tasks[ti]
+            if not _is_open(t, zoom):
+                continue
+            members, img, q, bookkeeping = self.form_squad(zoom, t, i, tasks, tasks_map, task_ids, bookkeeping)
+            task_ref.append(members)
+            imgs.append(img)
+            queries.append(q)
+            if len(task_ref) >= self.batch_size:
+                break
+        if not task_ref:
+            return [], [], []
+        longest = max(q.shape[1] for q in queries)
+        queries = [torch.cat([q, torch.zeros([1, longest - q.shape[1], 2])], axis=1) for q in queries]
+        return task_ref, torch.stack(imgs), torch.cat(queries)
+
+    def cotr_corr_multiscale(self, img_a, img_b, zoom_ins=[1.0], converge_iters=1, max_corrs=1000, queries_a=None,
+                             return_idx=False, force=False, return_tasks_only=False, areas=None):
+        img_a = img_a.copy()
+        img_b = img_b.copy()
+        if queries_a is not None:
+            queries_a = queries_a.copy()
+        tasks = self.gen_tasks(img_a, img_b, zoom_ins, converge_iters, max_corrs, queries_a, force, areas)
+        for zm in zoom_ins:
+            print(f'======= Zoom: {zm} ======')
+            while True:
+                num_g = self.num_good_tasks(tasks)
+                task_ref, img_batch, query_batch = self.form_grouped_batch(zm, tasks)
+                if len(task_ref) == 0 or num_g >= max_corrs:
+                    break
+                out = self.infer_batch_grouped(img_batch, query_batch)
+                num_steps = 0
+                for i, squad in enumerate(task_ref):
+                    for j, t in enumerate(squad):
+                        t.step(out[i, j])
+                        num_steps += 1
+                print(f'solved {num_steps} sub-tasks in one invocation with {img_batch.shape[0]} image pairs')
+                if num_steps <= self.batch_size:     # grouping no longer pays at this level (:398-399)
+                    break
+        # one-query-per-context fallback, only for tasks sitting at the LAST zoom value (:401-411)
+        self._single_query_loop(tasks, max_corrs, zm)
+        return self._finish(tasks, max_corrs, return_idx, force, return_tasks_only, img_a.shape[:2], img_b.shape[:2])

@@ -1,0 +1,125 @@
+/*
+ * cotr_b200 - C ABI of the B200-native COTR correspondence-inference hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The
+ * reference (ubc-vision/COTR) is pure Python, so "what its FFI would bind" is
+ * the L4->L3 call of the inference loop and the model construction protocol:
+ *
+ *   cotr_create            <- COTR/models/__init__.py:9-10  build_model(args)  +
+ *                             COTR/utils/utils.py:164-193   safe_load_weights(model, state_dict)
+ *                             (tensors are named by the reference's state_dict keys)
+ *   cotr_forward           <- COTR/models/cotr_model.py:26-40  COTR.forward(samples, queries)
+ *                             as called by sparse_engine.py:52,281 and inference_helper.py:126,134,197-198
+ *   cotr_encode_context    <- the query-independent part of COTR.forward: backbone.py:79-92,
+ *                             cotr_model.py:37 (input_proj), transformer.py:55 (encoder) and the K/V
+ *                             in-projections inside transformer.py:192-195
+ *   cotr_decode            <- the per-query part: cotr_model.py:34-36 (query_proj), transformer.py:56-57
+ *                             (decoder), cotr_model.py:38-39 (corr_embed, last level only)
+ *   cotr_forward_host      <- the same call with HOST buffers, i.e. including the .to(device) /
+ *                             .cpu() copies of sparse_engine.py:50-53
+ *
+ * All device pointers are fp32, contiguous.  Every call returns 0 on success; on failure it returns
+ * non-zero and cotr_last_error() describes the problem (the Python wrapper raises the exception type
+ * the reference would: AssertionError for a wrong canvas size, RuntimeError otherwise).
+ *
+ * Threading: one caller thread per model handle; one handle per device.  No hidden host syncs in the
+ * device-pointer calls (work is enqueued on the caller's stream) except when the internal workspace has
+ * to grow (first call / larger B or Q than seen before).
+ */
+#ifndef COTR_B200_H_
+#define COTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COTR_CANVAS_H 256          /* COTR/utils/constants.py:2  MAX_SIZE            */
+#define COTR_CANVAS_W 512          /* backbone.py:80             2 * MAX_SIZE        */
+#define COTR_CONTEXT_TOKENS 512    /* 16 x 32 layer3 grid                            */
+#define COTR_D_MODEL 256
+
+typedef struct cotr_model cotr_model;       /* opaque: packed weights + workspace, bound to one device */
+typedef struct cotr_context cotr_context;   /* opaque: per-pair decoder K/V cache (6 layers)           */
+
+/* One named host tensor of the reference checkpoint (fp32, C-contiguous). */
+typedef struct cotr_tensor {
+    const char* name;        /* reference state_dict key, e.g. "transformer.encoder.layers.0.linear1.weight" */
+    const float* data;       /* host pointer                                                                  */
+    int32_t ndim;
+    int64_t shape[4];
+} cotr_tensor;
+
+/* Build a model on CUDA device `device` from the 381 tensors of the reference state_dict
+ * (FrozenBN buffers included; the unused decoder norm1.* entries may be present and are ignored).
+ * Folds FrozenBN (backbone.py:46-56) into the conv kernels, repacks everything into kernel-native
+ * layouts and uploads.  Fails if a required key is missing or has the wrong shape. */
+int cotr_create(int device, const cotr_tensor* tensors, int n_tensors, cotr_model** out);
+void cotr_destroy(cotr_model* m);
+
+/* A context holds the K/V projections of all 6 decoder layers for up to `max_pairs` image pairs. */
+int cotr_context_create(cotr_model* m, int max_pairs, cotr_context** out);
+void cotr_context_destroy(cotr_context* c);
+
+/* img_dev: (B,3,256,512) NCHW fp32, ImageNet-normalised, the two 256x256 images side by side. */
+int cotr_encode_context(cotr_model* m, const float* img_dev, int B, cotr_context* ctx, void* cuda_stream);
+
+/* queries_dev: (B,Q,2) fp32 (x over the 512-wide canvas, y over 256, both normalised to [0,1]);
+ * pred_dev: (B,Q,2) fp32.  B must equal the B of the last cotr_encode_context on `ctx`. */
+int cotr_decode(cotr_model* m, const cotr_context* ctx, const float* queries_dev, int B, int Q,
+                float* pred_dev, void* cuda_stream);
+
+/* cotr_encode_context + cotr_decode on an internal context. */
+int cotr_forward(cotr_model* m, const float* img_dev, const float* queries_dev, int B, int Q,
+                 float* pred_dev, void* cuda_stream);
+
+/* Same with host buffers (pinned or pageable): H2D, forward, D2H, stream synchronised on return. */
+int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries_host, int B, int Q,
+                      float* pred_host);
+
+/* Bytes of device workspace a (B,Q) call needs (activations only, excluding weights and contexts). */
+size_t cotr_workspace_bytes(int B, int Q);
+
+/* Number of kernels the last cotr_forward / encode / decode call launched (for bench.py's gpu_launches). */
+int cotr_last_launch_count(const cotr_model* m);
+
+/* Test hook: copy an intermediate of the LAST forward to the host.  name is one of
+ * "feat" (2B,16,16,1024 NHWC, image n = 2*pair + half), "src" / "mem" (B*512,256 token-major),
+ * "hs" (B*Q,256, final decoder LayerNorm output; only valid if B*Q fits in one decode chunk).
+ * Returns the element count copied, or -1. */
+int64_t cotr_debug_read(cotr_model* m, const char* name, float* out_host, int64_t max_elems);
+
+/* Select the matrix-multiply path: 0 = tcgen05 tensor-core kernels (default), 1 = fp32 SIMT kernels
+ * (debug / numerical cross-check only). */
+int cotr_set_gemm_path(cotr_model* m, int path);
+
+/* ---- kernel-level test hooks (used by tests/ only) ------------------------------------------------------ */
+typedef struct cotr_test_gemm_desc {
+    int32_t path;                 /* 0 = tcgen05, 1 = fp32 SIMT                                               */
+    int32_t M, N, K;
+    int32_t a_mode;               /* 0 row-major [M,K]; 1 implicit im2col over NHWC; 2 stem NCHW canvas; 3 token gather */
+    int32_t lda;
+    int32_t H, W, C, OH, OW, KH, KW, stride, pad;   /* convolution geometry for a_mode 1 / 2                  */
+    int32_t relu;
+    int32_t add_period, ld_add, ldr, ldc;
+} cotr_test_gemm_desc;
+/* out = epilogue(A * W^T): A/bias/addmat/residual/ln_* /out are DEVICE pointers (may be NULL where optional),
+ * w_host is a HOST [N,K] matrix (packed for the tensor-core path internally). */
+int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float* w_host, const float* bias_dev,
+                   const float* addmat_dev, const float* residual_dev, const float* ln_gamma_dev,
+                   const float* ln_beta_dev, float* out_dev);
+/* out[(p*nq+i), h*32+d] = softmax(q k^T) v per head; q (npairs*nq,256), k/v (npairs*512,256), all DEVICE, ld 256. */
+int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const float* v_dev, float* out_dev,
+                        int nq, int npairs);
+/* bring-up switch for the shared-memory matrix descriptors (bit0: swap LBO/SBO). */
+void cotr_debug_set_variant(int variant);
+
+const char* cotr_last_error(void);
+const char* cotr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COTR_B200_H_ */

@@ -1,0 +1,192 @@
+"""GPU bring-up diagnostics (run under gpurun).  Each stage runs in its own process under a timeout so that a hung
+kernel cannot take the whole call down; results are appended to gpurun_out/bringup.log.
+
+    python tools/bringup.py            # all stages
+    python tools/bringup.py <stage>    # one stage in-process
+"""
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+OUT = os.path.join(REPO, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+
+STAGES = ["gemm_simt", "attn_simt", "gemm_tc_v0", "gemm_tc_v1", "attn_tc", "model_simt", "model_tc", "timing"]
+
+
+def _err(a, b):
+    a = a.double(); b = b.double()
+    return (a - b).abs().max().item(), ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def gemm_cases(path, variant=0):
+    import torch
+    import torch.nn.functional as F
+    from cotr_b200 import capi
+    capi.lib().cotr_debug_set_variant(variant)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    dev = "cuda"
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    worst = 0.0
+    # plain GEMMs (row-major A)
+    for (M, N, K) in [(128, 64, 64), (128, 64, 128), (256, 64, 256), (512, 256, 256), (1024, 1024, 256), (512, 256, 1024),
+                      (1000, 768, 256), (37, 2, 256), (8192, 64, 256), (300, 3072, 256)]:
+        A = rnd(M, K).to(dev); W = rnd(N, K) * 0.1; bias = rnd(N).to(dev)
+        ref = (A.double() @ W.to(dev).double().t() + bias.double()).relu()
+        out = capi.test_gemm(path, A, W.numpy(), bias=bias, relu=True)
+        e = _err(out, ref); worst = max(worst, e[1])
+        print(f"  gemm path={path} v={variant} M={M} N={N} K={K}: max {e[0]:.3e} rel {e[1]:.3e}", flush=True)
+    # residual + addmat + LayerNorm epilogue
+    M, N, K = 700, 256, 1024
+    A = rnd(M, K).to(dev); W = rnd(N, K) * 0.05; bias = rnd(N).to(dev); res = rnd(M, N).to(dev)
+    gam = (1 + 0.1 * rnd(N)).to(dev); bet = (0.1 * rnd(N)).to(dev)
+    ref = F.layer_norm(A.double() @ W.to(dev).double().t() + bias.double() + res.double(), (N,), gam.double(), bet.double(), 1e-5)
+    out = capi.test_gemm(path, A, W.numpy(), bias=bias, residual=res, ln=(gam, bet))
+    e = _err(out, ref); worst = max(worst, e[1])
+    print(f"  gemm+res+LN path={path}: max {e[0]:.3e} rel {e[1]:.3e}", flush=True)
+    M, N, K = 1024, 768, 256
+    A = rnd(M, K).to(dev); W = rnd(N, K) * 0.05; add = rnd(512, N).to(dev)
+    ref = A.double() @ W.to(dev).double().t() + add.double().repeat(2, 1)
+    out = capi.test_gemm(path, A, W.numpy(), addmat=add, add_period=512)
+    e = _err(out, ref); worst = max(worst, e[1])
+    print(f"  gemm+addmat path={path}: max {e[0]:.3e} rel {e[1]:.3e}", flush=True)
+    # implicit-GEMM convolutions (NHWC)
+    for (n, H, C, Co, k, s, pd) in [(2, 16, 64, 64, 3, 1, 1), (2, 32, 128, 128, 3, 2, 1), (2, 16, 256, 256, 3, 2, 1), (2, 32, 256, 512, 1, 2, 0)]:
+        x = rnd(n, C, H, H); w = rnd(Co, C, k, k) * 0.05; bias = rnd(Co).to(dev)
+        ref = F.conv2d(x.to(dev).double(), w.to(dev).double(), bias.double(), stride=s, padding=pd).permute(0, 2, 3, 1).reshape(-1, Co)
+        OH = (H + 2 * pd - k) // s + 1
+        xn = x.permute(0, 2, 3, 1).contiguous().to(dev)
+        wk = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+        out = capi.test_gemm(path, xn, wk.numpy(), bias=bias, a_mode=1, M=n * OH * OH,
+                             conv=dict(H=H, W=H, C=C, OH=OH, OW=OH, KH=k, KW=k, stride=s, pad=pd))
+        e = _err(out, ref); worst = max(worst, e[1])
+        print(f"  conv path={path} C={C}->{Co} k={k} s={s}: max {e[0]:.3e} rel {e[1]:.3e}", flush=True)
+    # stem: 7x7/2 over the NCHW canvas, halves as separate images
+    img = rnd(1, 3, 256, 512); w = rnd(64, 3, 7, 7) * 0.1; bias = rnd(64).to(dev)
+    halves = torch.cat([img[..., :256], img[..., 256:]], 0)
+    ref = F.conv2d(halves.to(dev).double(), w.to(dev).double(), bias.double(), stride=2, padding=3).relu().permute(0, 2, 3, 1).reshape(-1, 64)
+    wk = w.permute(0, 2, 3, 1).reshape(64, -1).contiguous()
+    out = capi.test_gemm(path, img.to(dev), wk.numpy(), bias=bias, relu=True, a_mode=2, M=2 * 128 * 128,
+                         conv=dict(H=256, W=256, C=3, OH=128, OW=128, KH=7, KW=7, stride=2, pad=3))
+    e = _err(out, ref); worst = max(worst, e[1])
+    print(f"  stem path={path}: max {e[0]:.3e} rel {e[1]:.3e}", flush=True)
+    print(f"WORST rel {worst:.3e}", flush=True)
+
+
+def attn_cases(path):
+    import torch
+    from cotr_b200 import capi
+    g = torch.Generator(device="cpu").manual_seed(1)
+    dev = "cuda"
+    for (nq, npairs, gain) in [(512, 1, 1.0), (1024, 2, 2.0), (100, 3, 1.0), (257, 1, 3.0), (1, 4, 1.0)]:
+        q = (torch.randn(npairs * nq, 256, generator=g) * gain).to(dev)
+        k = torch.randn(npairs * 512, 256, generator=g).to(dev)
+        v = torch.randn(npairs * 512, 256, generator=g).to(dev)
+        qh = q.double().view(npairs, nq, 8, 32).transpose(1, 2)
+        kh = k.double().view(npairs, 512, 8, 32).transpose(1, 2)
+        vh = v.double().view(npairs, 512, 8, 32).transpose(1, 2)
+        ref = (torch.softmax(qh @ kh.transpose(-1, -2), -1) @ vh).transpose(1, 2).reshape(npairs * nq, 256)
+        out = capi.test_attention(path, q, k, v, nq, npairs)
+        e = _err(out, ref)
+        print(f"  attention path={path} nq={nq} pairs={npairs} gain={gain}: max {e[0]:.3e} rel {e[1]:.3e}", flush=True)
+
+
+def model_case(path):
+    import torch
+    from cotr_b200.models import build_model
+    from oracle import cotr_oracle, fixtures
+    sd = fixtures.make_state_dict(0)
+    img, q = fixtures.make_inputs(1, 1, 1024)
+    model = build_model(None)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.cuda().eval()
+    model.native().set_gemm_path(path)
+    pred = model(torch.from_numpy(img).cuda(), torch.from_numpy(q).cuda())["pred_corrs"].cpu()
+    o32, inter = cotr_oracle.forward(sd, img, q, torch.float32, return_intermediates=True)
+    o64 = cotr_oracle.forward(sd, img, q, torch.float64)
+    nat = model.native()
+    feat = torch.from_numpy(nat.debug_read("feat", 2 * 16 * 16 * 1024)).view(2, 16, 16, 1024)
+    feat = torch.cat([feat[0], feat[1]], dim=1).permute(2, 0, 1)[None]          # (1,1024,16,32)
+    src = torch.from_numpy(nat.debug_read("src", 512 * 256)).view(1, 512, 256)
+    mem = torch.from_numpy(nat.debug_read("mem", 512 * 256)).view(1, 512, 256)
+    hs = torch.from_numpy(nat.debug_read("hs", 1024 * 256)).view(1, 1024, 256)
+    pos = torch.from_numpy(nat.debug_read("pos", 512 * 256)).view(512, 256)
+    for name, mine, ref in (("pos", pos, inter["pos"]), ("feat", feat, inter["feat"]), ("src", src, inter["src"]),
+                            ("mem", mem, inter["mem"]), ("hs", hs, inter["hs"])):
+        e = _err(mine, ref)
+        print(f"  {name}: max {e[0]:.3e} rel {e[1]:.3e}", flush=True)
+    print(f"  pred vs oracle fp32: max {(pred - o32).abs().max().item():.3e}; vs fp64: {(pred.double() - o64).abs().max().item():.3e}; "
+          f"oracle32 vs 64: {(o32.double() - o64).abs().max().item():.3e}; launches {nat.last_launch_count()}", flush=True)
+    gold = np.load(os.path.join(REPO, "tests", "golden", "model_b1_q1024.npz"))
+    print(f"  pred vs golden ref fp32: {np.abs(pred.numpy() - gold['ref_pred_fp32']).max():.3e}", flush=True)
+
+
+def timing():
+    import torch
+    from cotr_b200.models import build_model
+    from oracle import fixtures
+    sd = fixtures.make_state_dict(0)
+    model = build_model(None)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.cuda().eval()
+    for path in (1, 0):
+        model.native().set_gemm_path(path)
+        for (B, Q) in ((1, 1024), (8, 1024), (32, 1), (1, 16384)):
+            img, q = fixtures.make_inputs(1, B, Q)
+            img = torch.from_numpy(img).cuda(); q = torch.from_numpy(q).cuda()
+            for _ in range(3):
+                model(img, q)
+            torch.cuda.synchronize()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            n = 10
+            t0.record()
+            for _ in range(n):
+                model(img, q)
+            t1.record(); torch.cuda.synchronize()
+            ms = t0.elapsed_time(t1) / n
+            print(f"  path={path} B={B} Q={Q}: {ms:.3f} ms/forward  {B * Q / ms * 1e3:.0f} q/s  launches {model.native().last_launch_count()}", flush=True)
+
+
+def run_stage(name):
+    if name == "gemm_simt":
+        gemm_cases(1)
+    elif name == "attn_simt":
+        attn_cases(1)
+    elif name == "gemm_tc_v0":
+        gemm_cases(0, 0)
+    elif name == "gemm_tc_v1":
+        gemm_cases(0, 1)
+    elif name == "attn_tc":
+        attn_cases(0)
+    elif name == "model_simt":
+        model_case(1)
+    elif name == "model_tc":
+        model_case(0)
+    elif name == "timing":
+        timing()
+    else:
+        raise SystemExit(f"unknown stage {name}")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        run_stage(sys.argv[1])
+        sys.exit(0)
+    log = open(os.path.join(OUT, "bringup.log"), "a")
+    for st in STAGES:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), st], capture_output=True, text=True, timeout=240)
+            tail = r.stdout + ("\nSTDERR:\n" + r.stderr[-3000:] if r.returncode else "")
+            status = f"rc={r.returncode}"
+        except subprocess.TimeoutExpired as e:
+            tail = (e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")) + "\nTIMEOUT"
+            status = "TIMEOUT"
+        msg = f"=== {st}: {status} ({time.time() - t0:.1f}s)\n{tail}\n"
+        print(msg, flush=True)
+        log.write(msg); log.flush()
