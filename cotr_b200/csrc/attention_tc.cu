@@ -5,8 +5,10 @@
 //   warps 0-3  stage Q, K and V^T of this head as fp16 hi/lo core-matrix tiles (fp32-faithful 3-product scheme,
 //              see gemm_tc.cu), then run the softmax straight out of TMEM - each thread owns one query row, so the
 //              row max / row sum need no cross-thread reduction - and hand P to the MMA in 64-key chunks (double buffered);
-//   warp 4     (one lane) issues the tcgen05 MMAs: 2 x (128x256x32) for S, then 8 x (128x32x64) for O = P V, with the
-//              O accumulator re-using TMEM columns [0,32) once the first P chunk has been extracted from them.
+//   warp 4     (one lane) issues the tcgen05 MMAs: 2 x (128x256x32) for S, then 8 x (128x32x64) for O = P V.  The O
+//              accumulators re-use TMEM columns of S chunks that have already been turned into P: because the tensor
+//              core's fp32 accumulate truncates (profiles/r01_tc_precision.md) the hi*hi products alternate between
+//              two accumulators ([0,32) and [64,96)) and the small correction products go to a third ([32,64)).
 // q is expected pre-scaled by head_dim^-0.5 (folded into the projection weights).
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -211,9 +213,13 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         float* dst = p.out + grow * p.ldo + head * kHeadDim;
 #pragma unroll
         for (int c = 0; c < kHeadDim; c += 16) {
-            float v[16];
+            float v[16], w1[16], w2[16];
             __syncwarp();
             tmem_ld16(trow + c, v);
+            tmem_ld16(trow + 64 + c, w1);
+            tmem_ld16(trow + 32 + c, w2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (v[j] + w1[j]) + w2[j];
             if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
@@ -255,9 +261,11 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                     const uint32_t va = sbase + kOffV + (c * (kChunk / 8) + ks * 2) * kVLbo;
                     const uint64_t ph = desc(pa, kPLbo, kSbo, variant), pl = desc(pa + kPPlane, kPLbo, kSbo, variant);
                     const uint64_t vh = desc(va, kVLbo, kSbo, variant), vl = desc(va + kVPlane, kVLbo, kSbo, variant);
-                    umma_f16_ss(tmem_base, pl, vh, idesc_o, (c | ks) != 0);
-                    umma_f16_ss(tmem_base, ph, vl, idesc_o, true);
-                    umma_f16_ss(tmem_base, ph, vh, idesc_o, true);
+                    // chunk c may only touch TMEM columns of S chunks <= c (already consumed by the softmax warps)
+                    const uint32_t o_main = tmem_base + ((c & 1) ? 64u : 0u);
+                    umma_f16_ss(tmem_base + 32u, pl, vh, idesc_o, (c | ks) != 0);
+                    umma_f16_ss(tmem_base + 32u, ph, vl, idesc_o, true);
+                    umma_f16_ss(o_main, ph, vh, idesc_o, (c >= 2) || ks != 0);
                 }
                 umma_commit(&p_empty[buf]);
             }

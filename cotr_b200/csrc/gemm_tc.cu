@@ -42,7 +42,12 @@ struct Cfg {
     static constexpr uint32_t kStage = 2 * kAPlane + 2 * kBPlane;
     static constexpr int kStagesRaw = (int)((227u * 1024u - 2048u) / kStage);
     static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;
-    static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+    // The tensor core adds into its fp32 accumulator with truncation (measured: relative error grows ~1e-7 per
+    // chained MMA, profiles/r01_tc_precision.md).  K steps are therefore dealt round-robin onto kMainAcc TMEM
+    // accumulators and the small hi*lo / lo*hi products onto a separate one; the epilogue adds them up in fp32 RN.
+    static constexpr int kMainAcc = BN >= 256 ? 1 : (BN >= 128 ? 3 : 4);
+    static constexpr uint32_t kAccCols = (kMainAcc + 1) * BN;
+    static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
     static constexpr uint32_t kSmemBytes = kStages * kStage + 1024;
     static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         // ================= epilogue: TMEM -> registers -> global =============================================
         mbar_wait(accum_full, 0);
         tcgen05_fence_after();
+        const int n_ksteps = KC * (BK / 16);
         const int row = m0 + warp * 32 + lane;
         const bool row_ok = row < p.M;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -171,7 +177,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
+                __syncwarp();
                 tmem_ld16(trow + c, v);
+#pragma unroll
+                for (int a = 1; a <= C::kMainAcc; ++a) {
+                    if (a < C::kMainAcc && a >= n_ksteps) continue;     // accumulator never written (tiny K)
+                    float w2[16];
+                    tmem_ld16(trow + a * BN + c, w2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += w2[j];
+                }
                 if (!row_ok) continue;
                 const int nb = n0 + c;
                 if (nb >= p.N) continue;
@@ -210,7 +225,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
+                __syncwarp();
                 tmem_ld16(trow + c, v);
+#pragma unroll
+                for (int a = 1; a <= C::kMainAcc; ++a) {
+                    if (a < C::kMainAcc && a >= n_ksteps) continue;     // accumulator never written (tiny K)
+                    float w2[16];
+                    tmem_ld16(trow + a * BN + c, w2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += w2[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float x = v[j] * p.acc_scale;
@@ -228,6 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
+                __syncwarp();
                 tmem_ld16(trow + c, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -239,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
+                __syncwarp();
                 tmem_ld16(trow + c, v);
                 if (!row_ok) continue;
 #pragma unroll
@@ -293,9 +319,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                         dah = make_smem_desc(a_hi + ao, kALbo, kSbo); dal = make_smem_desc(a_lo + ao, kALbo, kSbo);
                         dbh = make_smem_desc(b_hi + bo, b_lbo, kSbo); dbl = make_smem_desc(b_lo + bo, b_lbo, kSbo);
                     }
-                    umma_f16_ss(tmem_base, dal, dbh, idesc, (it | ks) != 0);   // small terms first
-                    umma_f16_ss(tmem_base, dah, dbl, idesc, true);
-                    umma_f16_ss(tmem_base, dah, dbh, idesc, true);
+                    const int g = it * (BK / 16) + ks;                       // global K step
+                    const uint32_t main_acc = tmem_base + (uint32_t)(g % C::kMainAcc) * BN;
+                    const uint32_t corr_acc = tmem_base + (uint32_t)C::kMainAcc * BN;
+                    umma_f16_ss(corr_acc, dal, dbh, idesc, g != 0);
+                    umma_f16_ss(corr_acc, dah, dbl, idesc, true);
+                    umma_f16_ss(main_acc, dah, dbh, idesc, g >= C::kMainAcc);
                 }
                 umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
             }

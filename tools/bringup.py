@@ -78,6 +78,29 @@ def gemm_cases(path, variant=0):
     print(f"WORST rel {worst:.3e}", flush=True)
 
 
+def tc_precision():
+    """Where does the tcgen05 GEMM error come from?  fp16-exact operands isolate the accumulate; variants: 0 = split
+    accumulators (default), 2 = hi*hi only, 4 = everything chained on one accumulator."""
+    import torch
+    from cotr_b200 import capi
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for K in (64, 256, 1024, 2304):
+        M, N = 256, 128
+        A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g)
+        A16 = A.half().float(); W16 = (W.half().float())          # exactly representable: lo terms vanish
+        for name, a, w, variants in (("fp16-exact", A16, W16, (2, 0, 4)), ("fp32", A, W, (0, 4)), ("fp32 positive", A.abs(), W.abs(), (0, 4))):
+            ref = a.cuda().double() @ w.cuda().double().t()
+            for v in variants:
+                capi.lib().cotr_debug_set_variant(v)
+                out = capi.test_gemm(0, a.cuda(), w.numpy())
+                e = _err(out, ref)
+                bias = ((out.double() - ref) / ref.abs().clamp_min(1e-9)).mean().item()
+                print(f"  K={K:5d} {name:14s} variant={v}: rel {e[1]:.3e}  mean signed rel err {bias:+.3e}", flush=True)
+            out = capi.test_gemm(1, a.cuda(), w.numpy())
+            print(f"  K={K:5d} {name:14s} simt fp32 : rel {_err(out, ref)[1]:.3e}", flush=True)
+    capi.lib().cotr_debug_set_variant(0)
+
+
 def attn_cases(path):
     import torch
     from cotr_b200 import capi
@@ -169,6 +192,8 @@ def run_stage(name):
         model_case(0)
     elif name == "timing":
         timing()
+    elif name == "tc_precision":
+        tc_precision()
     else:
         raise SystemExit(f"unknown stage {name}")
 
