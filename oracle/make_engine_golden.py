@@ -21,6 +21,14 @@ from oracle.fake_model import FakeCOTR, synthetic_image  # noqa: E402
 ZOOMS = np.linspace(0.5, 0.0625, 4)
 
 
+def _plain(o):
+    """Numeric ndarray; task identifiers are None on the random-sampling path -> -1."""
+    a = np.asarray(o)
+    if a.dtype == object:
+        a = np.array([-1 if v is None else v for v in a.ravel()], dtype=np.float64).reshape(a.shape)
+    return a
+
+
 def scenarios(SparseEngine, FasterSparseEngine, cotr_flow, cotr_corr_base, fix_randomness):
     """name -> callable returning (list of result arrays, FakeCOTR)."""
     img_a = synthetic_image(11, 300, 400)      # non-square: two overlapping tiles each in 'tile' mode
@@ -37,7 +45,7 @@ def scenarios(SparseEngine, FasterSparseEngine, cotr_flow, cotr_corr_base, fix_r
             model = FakeCOTR()
             out = fn(model)
             out = list(out) if isinstance(out, (tuple, list)) else [out]
-            return [np.asarray(o) for o in out], model
+            return [_plain(o) for o in out], model
         return wrapped
 
     return {

@@ -47,9 +47,14 @@ def import_reference():
     if REF_ROOT in sys.path:
         sys.path.remove(REF_ROOT)
     sys.path.insert(0, REF_ROOT)
-    import COTR  # noqa: F401
-    assert os.path.realpath(COTR.__path__[0]).startswith(os.path.realpath(REF_ROOT)), COTR.__path__
-    return COTR
+    # The reference's COTR directory has no __init__.py (namespace package), so a regular package of the same name
+    # anywhere on sys.path - our alias package - would win.  Pin the package to the reference tree explicitly.
+    pkg = types.ModuleType("COTR")
+    pkg.__path__ = [os.path.join(REF_ROOT, "COTR")]
+    sys.modules["COTR"] = pkg
+    import COTR.models  # noqa: F401
+    assert os.path.realpath(sys.modules["COTR.models"].__file__).startswith(os.path.realpath(REF_ROOT))
+    return pkg
 
 
 def default_opt():
