@@ -25,6 +25,13 @@ class TestGemmDesc(ctypes.Structure):
         "relu", "add_period", "ld_add", "ldr", "ldc")]
 
 
+class LaunchRecord(ctypes.Structure):
+    _fields_ = [("kernel", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+                ("ms", ctypes.c_float)]
+
+
+KERNEL_NAMES = ("gemm_tc", "gemm_simt", "attention_tc", "attention_simt", "layernorm", "maxpool", "query_encode")
+
 # name -> (restype, argtypes); every symbol include/cotr_b200.h declares
 _PROTOTYPES = {
     "cotr_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(CotrTensor), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
@@ -37,11 +44,14 @@ _PROTOTYPES = {
     "cotr_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "cotr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "cotr_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "cotr_profile_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cotr_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(LaunchRecord), ctypes.c_int]),
     "cotr_debug_read": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
     "cotr_set_gemm_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cotr_test_gemm": (ctypes.c_int, [ctypes.POINTER(TestGemmDesc)] + [ctypes.c_void_p] * 8),
     "cotr_test_attention": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int]),
     "cotr_debug_set_variant": (None, [ctypes.c_int]),
+    "cotr_debug_set_timestamps": (None, [ctypes.c_void_p]),
     "cotr_last_error": (ctypes.c_char_p, []),
     "cotr_version": (ctypes.c_char_p, []),
 }
@@ -159,6 +169,19 @@ class NativeModel:
 
     def last_launch_count(self):
         return lib().cotr_last_launch_count(self.handle)
+
+    def profile_begin(self, max_records=4096):
+        check(lib().cotr_profile_begin(self.handle, int(max_records)), "cotr_profile_begin")
+        self._prof_max = int(max_records)
+
+    def profile_end(self):
+        """-> list of (kernel name, M, N, K, ms) for every launch since profile_begin, in launch order."""
+        buf = (LaunchRecord * self._prof_max)()
+        rc = lib().cotr_profile_end(self.handle, buf, self._prof_max)
+        if rc > 0:
+            raise RuntimeError(f"cotr_profile_end failed: {last_error()}")
+        n = -rc - 1
+        return [(KERNEL_NAMES[buf[i].kernel], buf[i].M, buf[i].N, buf[i].K, buf[i].ms) for i in range(n)]
 
     def debug_read(self, name, n_elems):
         out = np.empty(int(n_elems), dtype=np.float32)

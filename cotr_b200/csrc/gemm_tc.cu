@@ -3,17 +3,24 @@
 // Precision: the 1e-3 parity bar on predicted (x,y) rules out single-pass bf16 / tf32 / fp16 operands
 // (SURVEY.md appendix E.3).  Each fp32 operand is split into two fp16 terms (x ~= hi + lo, ~22 mantissa bits)
 // and the product is formed as  hi*hi + hi*lo + lo*hi  with fp32 accumulation in TMEM - three kind::f16 MMAs
-// per K step, ~2^-21 relative error per product.  Weights are pre-multiplied by a per-tensor power of two so
-// that their lo terms stay in fp16's normal range; the epilogue multiplies the accumulator by the inverse (exact).
+// per K step.  Weights are pre-multiplied by a per-tensor power of two so that their lo terms stay in fp16's
+// normal range; the epilogue multiplies the accumulator by the inverse (exact).  The tensor core adds into its fp32
+// accumulator with truncation (measured: ~1e-7 relative per chained MMA, profiles/r01_tc_precision.md), so the K steps
+// are dealt round-robin onto several TMEM accumulators and the small hi*lo / lo*hi products onto a separate one; the
+// epilogue adds them up with fp32 round-to-nearest.
 //
 // Data movement per CTA (one 128 x BN output tile, K walked in chunks of 64):
-//   * weights: pre-split, pre-tiled in HBM at model creation (tc_pack_weight) so that each pipeline stage is a
-//     handful of contiguous bulk-TMA copies (cp.async.bulk -> UBLKCP) straight into the UMMA canonical layout;
-//   * activations: warps 0-3 load fp32 (implicit im2col for the convolutions, a_loader.cuh), split to fp16
-//     hi/lo in registers and store 16-byte core-matrix rows to shared memory (conflict-free thanks to a padded LBO);
-//   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma and owns the TMEM allocation;
+//   * weights: pre-split, pre-tiled in HBM at model creation (tc_pack_weight) into 64-row x 64-k blocks that ARE the
+//     UMMA canonical shared-memory image, so a pipeline stage is BN/64 contiguous 16 KB bulk-TMA copies
+//     (cp.async.bulk -> UBLKCP) completing on an mbarrier;
+//   * activations: warps 0-3 load fp32 (implicit im2col for the convolutions), split to fp16 hi/lo in registers
+//     (loads for chunk i+1 are in flight while chunk i is converted) and store 16-byte core-matrix rows to shared
+//     memory (conflict-free thanks to a padded LBO);
+//   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma (N = 64 atoms) and owns TMEM;
 //   * warps 0-3 then run the epilogue out of TMEM: bias / constant add-matrix / residual / ReLU, or the fused
 //     residual + LayerNorm over the full 256-wide row (each thread owns one row, so no cross-thread reduction).
+// The kernel is templated on the A-operand addressing mode so that each instantiation carries exactly one loader
+// (an earlier all-modes-in-one kernel was ~30k SASS instructions and instruction-cache bound, profiles/r01_*).
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -24,6 +31,7 @@
 namespace cotr {
 
 int g_tc_variant = 0;   // bring-up switch: bit0 swaps the LBO / SBO fields of the shared-memory descriptors
+long long* g_tc_timestamps = nullptr;   // debug: 64 clock64() stamps per CTA (cotr_debug_set_timestamps), else null
 
 namespace {
 
@@ -36,27 +44,81 @@ constexpr uint32_t kALbo = BM * 16 + 16;       // padded: 8 lanes writing the 8 
 constexpr uint32_t kAPlane = 8 * kALbo;        // one fp16 plane (hi or lo) of the 128 x 64 A tile
 constexpr uint32_t kSbo = 128;                 // 8 rows x 16 bytes
 
+enum LoaderMode : int { LD_GATHER = 0, LD_CONV = 1, LD_GENERIC = 2 };
+
+__host__ __device__ inline int tc_npad(int N) { return N >= 64 ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16; }
+__host__ __device__ inline int tc_block_rows(int N) { return N >= 64 ? 64 : tc_npad(N); }
+
 template <int BN>
 struct Cfg {
-    static constexpr uint32_t kBPlane = BN * 128;                       // 8 K-groups x BN rows x 16 bytes
-    static constexpr uint32_t kStage = 2 * kAPlane + 2 * kBPlane;
+    static constexpr int kNB = BN >= 64 ? 64 : BN;                      // rows of one weight block == MMA N
+    static constexpr int kBlocks = BN / kNB;
+    static constexpr uint32_t kBBlock = 2u * 8u * kNB * 16u;            // [plane][K group][kNB rows][16 B]
+    static constexpr uint32_t kBStage = kBlocks * kBBlock;
+    static constexpr uint32_t kStage = 2 * kAPlane + kBStage;
     static constexpr int kStagesRaw = (int)((227u * 1024u - 2048u) / kStage);
     static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;
-    // The tensor core adds into its fp32 accumulator with truncation (measured: relative error grows ~1e-7 per
-    // chained MMA, profiles/r01_tc_precision.md).  K steps are therefore dealt round-robin onto kMainAcc TMEM
-    // accumulators and the small hi*lo / lo*hi products onto a separate one; the epilogue adds them up in fp32 RN.
     static constexpr int kMainAcc = BN >= 256 ? 1 : (BN >= 128 ? 3 : 4);
     static constexpr uint32_t kAccCols = (kMainAcc + 1) * BN;
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
     static constexpr uint32_t kSmemBytes = kStages * kStage + 1024;
     static_assert(kStages >= 2, "pipeline needs at least two stages");
+    static_assert(kAccCols <= 512, "TMEM has 512 columns");
 };
 
-__host__ __device__ inline int tc_npad(int N) { return N >= 64 ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16; }
+// ---- A-operand fetch: 8 rows x 8 consecutive k (two float4) per thread and K chunk ------------------------------
+template <int MODE>
+__device__ __forceinline__ void fetch_a(const GemmParams& p, const ARow (&rows)[8], int k0, int kg, float4 (&buf)[16]) {
+    if constexpr (MODE == LD_GATHER) {
+        const int k = k0 + kg * 8;
+        const bool k_ok = k < p.K;                 // K % 8 == 0 on this path
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (rows[i].valid && k_ok) {
+                v0 = __ldg(reinterpret_cast<const float4*>(rows[i].base + k));
+                v1 = __ldg(reinterpret_cast<const float4*>(rows[i].base + k + 4));
+            }
+            buf[2 * i] = v0;
+            buf[2 * i + 1] = v1;
+        }
+    } else if constexpr (MODE == LD_CONV) {
+        // C % 64 == 0: a 64-wide K chunk lies inside one filter tap
+        const int tap = k0 / p.C;
+        const int c0 = k0 - tap * p.C + kg * 8;
+        const int kh = tap / p.KW;
+        const int kw = tap - kh * p.KW;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            const int ih = rows[i].ih0 + kh, iw = rows[i].iw0 + kw;
+            if (rows[i].valid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                const float* src = rows[i].base + ((size_t)ih * p.W + iw) * p.C + c0;
+                v0 = __ldg(reinterpret_cast<const float4*>(src));
+                v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+            }
+            buf[2 * i] = v0;
+            buf[2 * i + 1] = v1;
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+            buf[2 * i] = load_a4(p, rows[i], k0 + kg * 8);
+            buf[2 * i + 1] = load_a4(p, rows[i], k0 + kg * 8 + 4);
+        }
+    }
+}
 
-template <int BN, bool LN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p, const int npad, const int variant) {
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <int BN, bool LN, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p, const int npad, const int variant,
+                                                              long long* __restrict__ ts) {
     using C = Cfg<BN>;
+    // debug timeline (ts != null): slot layout documented in tools/bringup.py::gemm_timeline
+    long long* my_ts = ts ? ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+    const long long t_start = ts ? clock64() : 0;
+#define COTR_TS(slot) do { if (my_ts) my_ts[(slot)] = clock64() - t_start; } while (0)
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
@@ -85,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 0) COTR_TS(1);
 
     if (warp < 4) {
         // ================= A producer: fp32 global -> fp16 hi/lo core-matrix rows in shared memory ============
@@ -94,55 +157,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         ARow rows[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rows[i] = decode_a_row(p, m0 + rb + 16 * i);
-        const bool gather = (p.a_mode == A_ROWMAJOR || p.a_mode == A_TOKENS);
-        const bool fast = gather ? ((p.K & 7) == 0 && (p.lda & 3) == 0) : (p.a_mode == A_CONV_NHWC && (p.C & 63) == 0);
-
-        // global loads of chunk `it` into registers (issued one chunk ahead of their use to keep loads in flight)
-        auto fetch = [&](int it, float4 (&buf)[16]) {
-            const int k0 = it * BK;
-            int kh = 0, kw = 0, c0 = 0;
-            if (!gather && fast) {     // a 64-wide K chunk lies inside one filter tap because C % 64 == 0
-                const int tap = k0 / p.C;
-                c0 = k0 - tap * p.C + kg * 8;
-                kh = tap / p.KW;
-                kw = tap - kh * p.KW;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                const ARow& r = rows[i];
-                if (fast) {
-                    if (gather) {
-                        const int k = k0 + kg * 8;
-                        if (r.valid && k < p.K) {
-                            v0 = __ldg(reinterpret_cast<const float4*>(r.base + k));
-                            v1 = __ldg(reinterpret_cast<const float4*>(r.base + k + 4));
-                        }
-                    } else {
-                        const int ih = r.ih0 + kh, iw = r.iw0 + kw;
-                        if (r.valid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
-                            const float* src = r.base + ((size_t)ih * p.W + iw) * p.C + c0;
-                            v0 = __ldg(reinterpret_cast<const float4*>(src));
-                            v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-                        }
-                    }
-                } else {
-                    v0 = load_a4(p, r, k0 + kg * 8);
-                    v1 = load_a4(p, r, k0 + kg * 8 + 4);
-                }
-                buf[2 * i] = v0;
-                buf[2 * i + 1] = v1;
-            }
-        };
 
         float4 cur[16], nxt[16];
-        fetch(0, cur);
+        fetch_a<MODE>(p, rows, 0, kg, cur);
+        if (threadIdx.x == 0) COTR_TS(2);
+#pragma unroll 1
         for (int it = 0; it < KC; ++it) {
             const int s = it % C::kStages;
             const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-            if (it + 1 < KC) fetch(it + 1, nxt);
+            if (it + 1 < KC) fetch_a<MODE>(p, rows, (it + 1) * BK, kg, nxt);
             mbar_wait(&empty[s], ph ^ 1u);
-            uint8_t* a_hi = stage_base + (size_t)s * C::kStage;
+            if (threadIdx.x == 0 && it < 8) COTR_TS(3 + 2 * it);
+            uint8_t* a_hi = stage_base + (size_t)s * C::kStage + (uint32_t)kg * kALbo + (uint32_t)rb * 16u;
             uint8_t* a_lo = a_hi + kAPlane;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -152,12 +178,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 split_f16x2(v0.z, v0.w, hi.y, lo.y);
                 split_f16x2(v1.x, v1.y, hi.z, lo.z);
                 split_f16x2(v1.z, v1.w, hi.w, lo.w);
-                const uint32_t off = (uint32_t)kg * kALbo + (uint32_t)(rb + 16 * i) * 16u;
-                *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                *reinterpret_cast<uint4*>(a_lo + off) = lo;
+                *reinterpret_cast<uint4*>(a_hi + i * 256) = hi;      // 16 rows x 16 bytes further down
+                *reinterpret_cast<uint4*>(a_lo + i * 256) = lo;
             }
             fence_proxy_async_smem();
             mbar_arrive(&full_a[s]);
+            if (threadIdx.x == 0 && it < 8) COTR_TS(4 + 2 * it);
 #pragma unroll
             for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }
@@ -165,52 +191,62 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         // ================= epilogue: TMEM -> registers -> global =============================================
         mbar_wait(accum_full, 0);
         tcgen05_fence_after();
-        const int n_ksteps = KC * (BK / 16);
+        if (threadIdx.x == 0) COTR_TS(20);
         const int row = m0 + warp * 32 + lane;
         const bool row_ok = row < p.M;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
         const float* add_row = (row_ok && p.addmat) ? p.addmat + (size_t)(row % p.add_period) * p.ld_add : nullptr;
         const float* res_row = (row_ok && p.residual) ? p.residual + (size_t)row * p.ldr : nullptr;
         float* out_row = p.out + (size_t)(row_ok ? row : 0) * p.ldc;
+        const float acc_scale = p.acc_scale;
+
+        // v[0..15] = sum over all accumulators of columns [c, c+16)
+        auto load_acc = [&](int c, float (&v)[16]) {
+            __syncwarp();
+            tmem_ld16(trow + c, v);
+#pragma unroll
+            for (int a = 1; a <= C::kMainAcc; ++a) {
+                float w2[16];
+                tmem_ld16(trow + a * BN + c, w2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += w2[j];
+            }
+        };
+        // x += src[0..15] (vectorised; all row operands are 16-byte aligned on this path)
+        auto add16 = [&](const float* src, float (&v)[16]) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 t4 = ldg4(src + j);
+                v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+            }
+        };
+
         if constexpr (!LN) {
-            const bool vec_ok = (p.ldc & 3) == 0;
+            const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 15) == 0 && (p.ld_add & 3) == 0 && (p.ldr & 3) == 0;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
-                __syncwarp();
-                tmem_ld16(trow + c, v);
-#pragma unroll
-                for (int a = 1; a <= C::kMainAcc; ++a) {
-                    if (a < C::kMainAcc && a >= n_ksteps) continue;     // accumulator never written (tiny K)
-                    float w2[16];
-                    tmem_ld16(trow + a * BN + c, w2);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += w2[j];
-                }
-                if (!row_ok) continue;
+                load_acc(c, v);
                 const int nb = n0 + c;
-                if (nb >= p.N) continue;
-                if (nb + 15 < p.N) {
+                if (!row_ok || nb >= p.N) continue;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x = v[j] * p.acc_scale;
-                        if (p.bias) x += __ldg(p.bias + nb + j);
-                        if (add_row) x += __ldg(add_row + nb + j);
-                        if (res_row) x += __ldg(res_row + nb + j);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        v[j] = x;
+                for (int j = 0; j < 16; ++j) v[j] *= acc_scale;
+                if (vec_ok) {
+                    if (p.bias) add16(p.bias + nb, v);
+                    if (add_row) add16(add_row + nb, v);
+                    if (res_row) add16(res_row + nb, v);
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-                    if (vec_ok) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(out_row + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) out_row[nb + j] = v[j];
-                    }
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(out_row + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
-                    for (int j = 0; j < 16 && nb + j < p.N; ++j) {
-                        float x = v[j] * p.acc_scale;
+#pragma unroll 1
+                    for (int j = 0; j < 16; ++j) {
+                        if (nb + j >= p.N) break;
+                        float x = v[j];
                         if (p.bias) x += __ldg(p.bias + nb + j);
                         if (add_row) x += __ldg(add_row + nb + j);
                         if (res_row) x += __ldg(res_row + nb + j);
@@ -225,25 +261,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
-                __syncwarp();
-                tmem_ld16(trow + c, v);
+                load_acc(c, v);
 #pragma unroll
-                for (int a = 1; a <= C::kMainAcc; ++a) {
-                    if (a < C::kMainAcc && a >= n_ksteps) continue;     // accumulator never written (tiny K)
-                    float w2[16];
-                    tmem_ld16(trow + a * BN + c, w2);
+                for (int j = 0; j < 16; ++j) v[j] *= acc_scale;
+                if (p.bias) add16(p.bias + c, v);
+                if (add_row) add16(add_row + c, v);
+                if (res_row) add16(res_row + c, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += w2[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float x = v[j] * p.acc_scale;
-                    if (p.bias) x += __ldg(p.bias + c + j);
-                    if (add_row) x += __ldg(add_row + c + j);
-                    if (res_row) x += __ldg(res_row + c + j);
-                    v[j] = x;
-                    sum += x;
-                }
+                for (int j = 0; j < 16; ++j) sum += v[j];
                 tmem_st16(trow + c, v);
             }
             tmem_st_wait();
@@ -268,67 +293,81 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 tmem_ld16(trow + c, v);
                 if (!row_ok) continue;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    v[j] = (v[j] - mean) * rstd * __ldg(p.ln_gamma + c + j) + __ldg(p.ln_beta + c + j);
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(out_row + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 g4 = ldg4(p.ln_gamma + c + j), b4 = ldg4(p.ln_beta + c + j);
+                    float4 o;
+                    o.x = (v[j] - mean) * rstd * g4.x + b4.x;
+                    o.y = (v[j + 1] - mean) * rstd * g4.y + b4.y;
+                    o.z = (v[j + 2] - mean) * rstd * g4.z + b4.z;
+                    o.w = (v[j + 3] - mean) * rstd * g4.w + b4.w;
+                    *reinterpret_cast<float4*>(out_row + c + j) = o;
+                }
             }
         }
+        if (threadIdx.x == 0) COTR_TS(21);
     } else if (warp == 4) {
         // ================= weight producer: bulk TMA of the pre-tiled fp16 hi/lo image ==========================
         if (lane == 0) {
             const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.Wtc);
+            const int blocks_total = npad / C::kNB;
+            const int blk0 = n0 / C::kNB;
+#pragma unroll 1
             for (int it = 0; it < KC; ++it) {
                 const int s = it % C::kStages;
                 const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_b[s], 2u * C::kBPlane);
+                mbar_arrive_expect_tx(&full_b[s], C::kBStage);
                 uint8_t* b_dst = stage_base + (size_t)s * C::kStage + 2 * kAPlane;
-                // image: [k chunk][plane][K group][npad rows][16 bytes]
-                const uint8_t* src = wimg + ((size_t)it * 16) * (size_t)npad * 16 + (size_t)n0 * 16;
-#pragma unroll 1
-                for (int j = 0; j < 16; ++j)
-                    tma_bulk_g2s(b_dst + (size_t)j * BN * 16, src + (size_t)j * npad * 16, BN * 16, &full_b[s]);
+                // image: [k chunk][64-row block][plane][K group][64 rows][16 bytes]; the blocks of one tile are adjacent
+                const uint8_t* src = wimg + ((size_t)it * blocks_total + blk0) * C::kBBlock;
+#pragma unroll
+                for (int j = 0; j < C::kBlocks; ++j)
+                    tma_bulk_g2s(b_dst + (size_t)j * C::kBBlock, src + (size_t)j * C::kBBlock, C::kBBlock, &full_b[s]);
+                if (it < 8) COTR_TS(44 + it);
             }
         }
         __syncwarp();
     } else {
         // ================= MMA issuer ===========================================================================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
-            const uint32_t b_lbo = BN * 16;
+            constexpr uint32_t idesc = make_idesc_f16_f32(BM, C::kNB);
+            constexpr uint32_t b_lbo = C::kNB * 16;
+            constexpr uint32_t b_plane = 8 * b_lbo;
+#pragma unroll 1
             for (int it = 0; it < KC; ++it) {
                 const int s = it % C::kStages;
                 const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
                 mbar_wait(&full_a[s], ph);
+                if (it < 8) COTR_TS(24 + 2 * it);
                 mbar_wait(&full_b[s], ph);
                 tcgen05_fence_after();
                 const uint32_t a_hi = smem_u32(stage_base + (size_t)s * C::kStage);
                 const uint32_t a_lo = a_hi + kAPlane;
-                const uint32_t b_hi = a_hi + 2 * kAPlane;
-                const uint32_t b_lo = b_hi + C::kBPlane;
+                const uint32_t b_base = a_hi + 2 * kAPlane;
 #pragma unroll
                 for (int ks = 0; ks < BK / 16; ++ks) {
-                    const uint32_t ao = ks * 2 * kALbo, bo = ks * 2 * b_lbo;
-                    uint64_t dah, dal, dbh, dbl;
-                    if (variant & 1) {
-                        dah = make_smem_desc(a_hi + ao, kSbo, kALbo); dal = make_smem_desc(a_lo + ao, kSbo, kALbo);
-                        dbh = make_smem_desc(b_hi + bo, kSbo, b_lbo); dbl = make_smem_desc(b_lo + bo, kSbo, b_lbo);
-                    } else {
-                        dah = make_smem_desc(a_hi + ao, kALbo, kSbo); dal = make_smem_desc(a_lo + ao, kALbo, kSbo);
-                        dbh = make_smem_desc(b_hi + bo, b_lbo, kSbo); dbl = make_smem_desc(b_lo + bo, b_lbo, kSbo);
-                    }
                     const int g = it * (BK / 16) + ks;                       // global K step
-                    const uint32_t main_acc = tmem_base + (uint32_t)(g % C::kMainAcc) * BN;
-                    const uint32_t corr_acc = tmem_base + (uint32_t)C::kMainAcc * BN;
-                    umma_f16_ss(corr_acc, dal, dbh, idesc, g != 0);
-                    umma_f16_ss(corr_acc, dah, dbl, idesc, true);
-                    umma_f16_ss(main_acc, dah, dbh, idesc, g >= C::kMainAcc);
+                    const uint32_t ao = ks * 2 * kALbo, bo = ks * 2 * b_lbo;
+                    const uint64_t dah = (variant & 1) ? make_smem_desc(a_hi + ao, kSbo, kALbo) : make_smem_desc(a_hi + ao, kALbo, kSbo);
+                    const uint64_t dal = (variant & 1) ? make_smem_desc(a_lo + ao, kSbo, kALbo) : make_smem_desc(a_lo + ao, kALbo, kSbo);
+                    const uint32_t main_col = (uint32_t)(g % C::kMainAcc) * BN;
+                    const uint32_t corr_col = (uint32_t)C::kMainAcc * BN;
+#pragma unroll
+                    for (int j = 0; j < C::kBlocks; ++j) {
+                        const uint32_t bh = b_base + j * C::kBBlock + bo, bl = bh + b_plane;
+                        const uint64_t dbh = (variant & 1) ? make_smem_desc(bh, kSbo, b_lbo) : make_smem_desc(bh, b_lbo, kSbo);
+                        const uint64_t dbl = (variant & 1) ? make_smem_desc(bl, kSbo, b_lbo) : make_smem_desc(bl, b_lbo, kSbo);
+                        const uint32_t col = tmem_base + j * C::kNB;
+                        umma_f16_ss(col + corr_col, dal, dbh, idesc, g != 0);
+                        umma_f16_ss(col + corr_col, dah, dbl, idesc, true);
+                        umma_f16_ss(col + main_col, dah, dbh, idesc, g >= C::kMainAcc);
+                    }
                 }
                 umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
+                if (it < 8) COTR_TS(25 + 2 * it);
             }
             umma_commit(accum_full);
+            COTR_TS(41);
         }
         __syncwarp();
     }
@@ -336,21 +375,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, C::kTmemCols);
+    if (threadIdx.x == 160) COTR_TS(60);
+#undef COTR_TS
 }
 
-template <int BN, bool LN>
+template <int BN, bool LN, int MODE>
 int launch_one(const GemmParams& p, cudaStream_t s) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        COTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+        COTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, LN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
         configured = true;
     }
     const int npad = tc_npad(p.N);
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-    gemm_tc_kernel<BN, LN><<<grid, kThreads, C::kSmemBytes, s>>>(p, npad, g_tc_variant);
+    gemm_tc_kernel<BN, LN, MODE><<<grid, kThreads, C::kSmemBytes, s>>>(p, npad, g_tc_variant, g_tc_timestamps);
     COTR_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int BN, bool LN>
+int launch_mode(const GemmParams& p, cudaStream_t s) {
+    const bool gather = (p.a_mode == A_ROWMAJOR || p.a_mode == A_TOKENS);
+    if (gather && (p.K & 7) == 0 && (p.lda & 3) == 0) return launch_one<BN, LN, LD_GATHER>(p, s);
+    if constexpr (!LN && BN >= 64) {
+        if (p.a_mode == A_CONV_NHWC && (p.C & 63) == 0) return launch_one<BN, LN, LD_CONV>(p, s);
+    }
+    if constexpr (!LN && BN == 64) return launch_one<64, false, LD_GENERIC>(p, s);
+    set_error("gemm_tc: no kernel instantiation for a_mode %d, K %d, lda %d with tile N %d", p.a_mode, p.K, p.lda, BN);
+    return 1;
 }
 
 inline uint16_t f32_to_f16_rn(float f) {     // round-to-nearest-even, saturating, subnormals supported
@@ -396,10 +449,13 @@ size_t tc_weight_bytes(int N, int K) {
     return kc * 16 * (size_t)tc_npad(N) * 16;
 }
 
-// Image layout: [k chunk (64)][plane: hi, lo][K group (8 halves)][npad rows][8 halves]; zero padded in N and K.
-// The matrix is multiplied by 2^e, e chosen so that max|w| * 2^e lies in [2^12, 2^13); returns 2^-e for the epilogue.
+// Image layout: [k chunk (64)][row block (64 rows; 16 when N < 64)][plane: hi, lo][K group (8 halves)][row][8 halves],
+// zero padded in N and K.  The matrix is multiplied by 2^e, e chosen so that max|w| * 2^e lies in [2^12, 2^13);
+// returns 2^-e for the epilogue.
 float tc_pack_weight(const float* w, int N, int K, void* dst_host) {
     const int npad = tc_npad(N);
+    const int nb = tc_block_rows(N);
+    const int blocks = npad / nb;
     const int kc_n = (K + BK - 1) / BK;
     float amax = 0.f;
     for (size_t i = 0; i < (size_t)N * K; ++i) amax = fmaxf(amax, fabsf(w[i]));
@@ -412,16 +468,19 @@ float tc_pack_weight(const float* w, int N, int K, void* dst_host) {
     const float scale = ldexpf(1.f, e);
     uint16_t* out = reinterpret_cast<uint16_t*>(dst_host);
     for (int kc = 0; kc < kc_n; ++kc)
-        for (int kg = 0; kg < 8; ++kg)
-            for (int n = 0; n < npad; ++n)
-                for (int el = 0; el < 8; ++el) {
-                    const int k = kc * BK + kg * 8 + el;
-                    const float x = (n < N && k < K) ? w[(size_t)n * K + k] * scale : 0.f;
-                    const uint16_t hi = f32_to_f16_rn(x);
-                    const uint16_t lo = f32_to_f16_rn(x - f16_to_f32(hi));
-                    out[((((size_t)kc * 2 + 0) * 8 + kg) * npad + n) * 8 + el] = hi;
-                    out[((((size_t)kc * 2 + 1) * 8 + kg) * npad + n) * 8 + el] = lo;
-                }
+        for (int b = 0; b < blocks; ++b)
+            for (int kg = 0; kg < 8; ++kg)
+                for (int r = 0; r < nb; ++r)
+                    for (int el = 0; el < 8; ++el) {
+                        const int n = b * nb + r;
+                        const int k = kc * BK + kg * 8 + el;
+                        const float x = (n < N && k < K) ? w[(size_t)n * K + k] * scale : 0.f;
+                        const uint16_t hi = f32_to_f16_rn(x);
+                        const uint16_t lo = f32_to_f16_rn(x - f16_to_f32(hi));
+                        const size_t blk = ((size_t)kc * blocks + b) * 2;
+                        out[(((blk + 0) * 8 + kg) * nb + r) * 8 + el] = hi;
+                        out[(((blk + 1) * 8 + kg) * nb + r) * 8 + el] = lo;
+                    }
     return ldexpf(1.f, -e);
 }
 
@@ -431,12 +490,16 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     COTR_CHECK(p.a_mode != A_CONV_NHWC || (p.C & 3) == 0, "gemm_tc: NHWC conv needs C %% 4 == 0 (C=%d)", p.C);
     if (p.ln_gamma) {
         COTR_CHECK(p.N == 256 && p.ldc == 256 && p.relu == 0, "gemm_tc: LayerNorm epilogue needs N = ldc = 256");
-        return launch_one<256, true>(p, s);
+        COTR_CHECK((p.ldr & 3) == 0 && (p.ld_add & 3) == 0, "gemm_tc: LayerNorm epilogue needs 16-byte aligned row operands");
+        return launch_mode<256, true>(p, s);
     }
-    if (p.N <= 16) return launch_one<16, false>(p, s);
+    if (p.N < 64) {
+        COTR_CHECK(p.N <= 16, "gemm_tc: N between 17 and 63 is not instantiated");
+        return launch_mode<16, false>(p, s);
+    }
     const int mt = (p.M + BM - 1) / BM;
-    if ((p.N % 128) == 0 && (long long)mt * (p.N / 128) >= 120) return launch_one<128, false>(p, s);
-    return launch_one<64, false>(p, s);
+    if ((p.N % 128) == 0 && (long long)mt * (p.N / 128) >= 120) return launch_mode<128, false>(p, s);
+    return launch_mode<64, false>(p, s);
 }
 
 }  // namespace cotr

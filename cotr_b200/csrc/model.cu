@@ -13,6 +13,7 @@
 namespace cotr {
 
 extern int g_tc_variant;
+extern long long* g_tc_timestamps;
 static thread_local char g_error[1024] = "";
 
 void set_error(const char* fmt, ...) {
@@ -109,6 +110,11 @@ struct cotr_model {
     const float* last_feat = nullptr;
     const float* last_mem = nullptr;
     int last_pairs = 0, last_rows = 0;
+    // per-launch profiler (cotr_profile_begin / cotr_profile_end): CUDA event pairs on the launching stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_events;      // 2 per record
+    std::vector<cotr_launch_record> prof_records;
+    int prof_max = 0;
 };
 
 namespace cotr {
@@ -227,6 +233,32 @@ struct Run {
     cudaStream_t s;
 };
 
+enum KernelId { K_GEMM_TC = 0, K_GEMM_SIMT = 1, K_ATTN_TC = 2, K_ATTN_SIMT = 3, K_LAYERNORM = 4, K_MAXPOOL = 5, K_QENC = 6 };
+
+// Counts the launch and, when the profiler is on, brackets it with two events on the launching stream.
+struct LaunchScope {
+    cotr_model* m;
+    cudaStream_t s;
+    int slot = -1;
+    LaunchScope(const Run& r, int kernel, int M, int N, int K) : m(r.m), s(r.s) {
+        m->launches++;
+        if (!m->prof_on || (int)m->prof_records.size() >= m->prof_max) return;
+        slot = (int)m->prof_records.size();
+        while ((int)m->prof_events.size() < 2 * (slot + 1)) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) { slot = -1; return; }
+            m->prof_events.push_back(e);
+        }
+        cotr_launch_record rec;
+        rec.kernel = kernel; rec.M = M; rec.N = N; rec.K = K; rec.ms = 0.f;
+        m->prof_records.push_back(rec);
+        cudaEventRecord(m->prof_events[2 * slot], s);
+    }
+    ~LaunchScope() {
+        if (slot >= 0) cudaEventRecord(m->prof_events[2 * slot + 1], s);
+    }
+};
+
 GemmParams gemm_base(int M, int N, int K, const float* A, int lda, const float* W, const void* Wtc, float wtc_scale,
                      float* out, int ldc) {
     GemmParams p;
@@ -243,7 +275,7 @@ GemmParams gemm_base(int M, int N, int K, const float* A, int lda, const float* 
 int run_gemm(const Run& r, GemmParams p, float* ln_scratch) {
     // The tensor-core GEMM fuses LayerNorm into its epilogue; the SIMT path runs it as a separate kernel.
     if (r.m->gemm_path == 0) {
-        r.m->launches++;
+        LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
         return launch_gemm_tc(p, r.s);
     }
     const float* g = p.ln_gamma;
@@ -254,10 +286,12 @@ int run_gemm(const Run& r, GemmParams p, float* ln_scratch) {
         p.ln_gamma = nullptr; p.ln_beta = nullptr;
         p.out = ln_scratch;
     }
-    r.m->launches++;
-    if (launch_gemm_simt(p, r.s)) return 1;
+    {
+        LaunchScope scope(r, K_GEMM_SIMT, p.M, p.N, p.K);
+        if (launch_gemm_simt(p, r.s)) return 1;
+    }
     if (g) {
-        r.m->launches++;
+        LaunchScope scope(r, K_LAYERNORM, p.M, kDModel, 0);
         if (launch_layernorm(ln_scratch, nullptr, g, b, final_out, p.M, r.s)) return 1;
     }
     return 0;
@@ -295,7 +329,8 @@ int run_conv(const Run& r, const DevConv& c, int n_img, const float* in, int H, 
 }
 
 int run_attention(const Run& r, const AttnParams& p) {
-    r.m->launches++;
+    // recorded as M = query rows, N = 512 keys, K = 32 x 8 heads
+    LaunchScope scope(r, r.m->gemm_path == 0 ? K_ATTN_TC : K_ATTN_SIMT, p.nq * p.npairs, kTokens, kDModel);
     if (r.m->gemm_path == 0) return launch_attention_tc(p, r.s);
     return launch_attention_simt(p, r.s);
 }
@@ -372,8 +407,10 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
     // backbone.py:81-82: the two 256x256 halves go through the ResNet body as independent images.
     // Stem: conv 7x7/2 (+FrozenBN folded) + ReLU, then MaxPool 3x3/2  (torchvision resnet.py _forward_impl).
     if (run_conv(r, m->stem, n_img, img, 256, 256, w.stem, true, nullptr, /*stem_nchw=*/true)) return 1;
-    m->launches++;
-    if (launch_maxpool_3x3s2_nhwc(w.stem, w.bx, n_img, 128, 128, 64, s)) return 1;
+    {
+        LaunchScope scope(r, K_MAXPOOL, n_img * 64 * 64, 64, 0);
+        if (launch_maxpool_3x3s2_nhwc(w.stem, w.bx, n_img, 128, 128, 64, s)) return 1;
+    }
 
     float* x = w.bx;
     float* y = w.by;
@@ -448,8 +485,10 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
     Run r{m, s};
     const int R = npairs * nq;
     // cotr_model.py:34-35 query_proj (lin_sine, depth 64)
-    m->launches++;
-    if (launch_query_encode(queries, w.qpos, R, s)) return 1;
+    {
+        LaunchScope scope(r, K_QENC, R, kDModel, 0);
+        if (launch_query_encode(queries, w.qpos, R, s)) return 1;
+    }
     // q-side of transformer.py:192: ((t + qpos) Wq^T + bq) s  =  t (s Wq)^T + [qpos (s Wq)^T + s bq]; the bracket for
     // all 6 layers is one GEMM.
     if (run_linear(r, m->qpos_all, R, w.qpos, kDModel, w.qp, kQpCols, false)) return 1;
@@ -476,8 +515,10 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
         if (run_linear(r, d.l2, R, w.dh, kFF, w.t, kDModel, false, w.t, kDModel, d.ln3_g, d.ln3_b, w.dtmp)) return 1;
     }
     // transformer.py:110-111 decoder.norm on the last level; cotr_model.py:38-39 corr_embed on that level only.
-    m->launches++;
-    if (launch_layernorm(w.t, nullptr, m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
+    {
+        LaunchScope scope(r, K_LAYERNORM, R, kDModel, 0);
+        if (launch_layernorm(w.t, nullptr, m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
+    }
     if (run_linear(r, m->head[0], R, w.hs, kDModel, w.hd1, kDModel, true)) return 1;
     if (run_linear(r, m->head[1], R, w.hd1, kDModel, w.hd2, kDModel, true)) return 1;
     if (run_linear(r, m->head[2], R, w.hd2, kDModel, pred, 2, false)) return 1;
@@ -684,6 +725,7 @@ void cotr_destroy(cotr_model* m) {
                       &w.img_stage, &w.q_stage, &w.pred_stage};
     for (float** b : bufs) ws_free(b);
     if (m->host_stream) cudaStreamDestroy(m->host_stream);
+    for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
     delete m;
 }
 
@@ -771,6 +813,31 @@ size_t cotr_workspace_bytes(int B, int Q) {
 
 int cotr_last_launch_count(const cotr_model* m) { return m ? m->launches : -1; }
 
+int cotr_profile_begin(cotr_model* m, int max_records) {
+    COTR_CHECK(m && max_records > 0, "cotr_profile_begin: bad arguments");
+    m->prof_records.clear();
+    m->prof_records.reserve(max_records);
+    m->prof_max = max_records;
+    m->prof_on = true;
+    return 0;
+}
+
+int cotr_profile_end(cotr_model* m, cotr_launch_record* out, int max_records) {
+    COTR_CHECK(m && out, "cotr_profile_end: bad arguments");
+    m->prof_on = false;
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    COTR_CHECK_CUDA(cudaDeviceSynchronize());
+    int n = (int)m->prof_records.size();
+    if (n > max_records) n = max_records;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        COTR_CHECK_CUDA(cudaEventElapsedTime(&ms, m->prof_events[2 * i], m->prof_events[2 * i + 1]));
+        m->prof_records[i].ms = ms;
+        out[i] = m->prof_records[i];
+    }
+    return n >= 0 ? -n - 1 : 1;     // see header: success is encoded as -(count + 1)
+}
+
 int64_t cotr_debug_read(cotr_model* m, const char* name, float* out_host, int64_t max_elems) {
     if (!m || !name || !out_host) return -1;
     cudaSetDevice(m->device);
@@ -795,6 +862,7 @@ int cotr_set_gemm_path(cotr_model* m, int path) {
 }
 
 void cotr_debug_set_variant(int variant) { g_tc_variant = variant; }
+void cotr_debug_set_timestamps(void* dev_buffer) { g_tc_timestamps = reinterpret_cast<long long*>(dev_buffer); }
 
 int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float* w_host, const float* bias_dev,
                    const float* addmat_dev, const float* residual_dev, const float* ln_gamma_dev,

@@ -85,6 +85,19 @@ size_t cotr_workspace_bytes(int B, int Q);
 /* Number of kernels the last cotr_forward / encode / decode call launched (for bench.py's gpu_launches). */
 int cotr_last_launch_count(const cotr_model* m);
 
+/* Per-launch profiler.  Between cotr_profile_begin and cotr_profile_end every kernel the library launches is bracketed
+ * by two CUDA events recorded on the launching stream.  cotr_profile_end synchronises the device, fills `out` with
+ * one record per launch in launch order and returns -(count + 1) on success (so 0 records -> -1), > 0 on failure.
+ * kernel ids: 0 gemm_tc (tcgen05), 1 gemm_simt, 2 attention_tc, 3 attention_simt, 4 layernorm, 5 maxpool,
+ * 6 query_encode.  For GEMMs M,N,K are the problem size; for attention M = query rows, N = 512, K = 256. */
+typedef struct cotr_launch_record {
+    int32_t kernel;
+    int32_t M, N, K;
+    float ms;
+} cotr_launch_record;
+int cotr_profile_begin(cotr_model* m, int max_records);
+int cotr_profile_end(cotr_model* m, cotr_launch_record* out, int max_records);
+
 /* Test hook: copy an intermediate of the LAST forward to the host.  name is one of
  * "feat" (2B,16,16,1024 NHWC, image n = 2*pair + half), "src" / "mem" (B*512,256 token-major),
  * "hs" (B*Q,256, final decoder LayerNorm output; only valid if B*Q fits in one decode chunk).
@@ -115,6 +128,9 @@ int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const 
                         int nq, int npairs);
 /* bring-up switch for the shared-memory matrix descriptors (bit0: swap LBO/SBO). */
 void cotr_debug_set_variant(int variant);
+/* debug timeline of the tcgen05 GEMM: DEVICE buffer of 64 int64 per CTA receiving clock64() deltas of the pipeline
+ * events of every following GEMM launch (NULL switches it off).  Slot layout: tools/bringup.py::gemm_timeline. */
+void cotr_debug_set_timestamps(void* dev_buffer);
 
 const char* cotr_last_error(void);
 const char* cotr_version(void);

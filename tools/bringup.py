@@ -101,6 +101,36 @@ def tc_precision():
     capi.lib().cotr_debug_set_variant(0)
 
 
+def gemm_timeline():
+    """clock64() timeline of one CTA of the tcgen05 GEMM (cotr_debug_set_timestamps).  Slots: 1 setup done; 2 first A
+    fetch issued; 3+2i loader got stage i; 4+2i loader published stage i; 20 accumulator ready (epilogue start);
+    21 epilogue done; 24+2i MMA saw A(i); 25+2i MMA issued + committed stage i; 41 final commit; 44+i TMA issued
+    stage i; 60 teardown done."""
+    import ctypes
+    import torch
+    from cotr_b200 import capi
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for (M, N, K, ln) in [(1024, 256, 256, False), (512, 1024, 256, False), (512, 256, 2304, False), (512, 256, 1024, True)]:
+        A = torch.randn(M, K, generator=g).cuda(); W = torch.randn(N, K, generator=g) * 0.1
+        bias = torch.randn(N, generator=g).cuda()
+        ln_args = (torch.ones(N).cuda(), torch.zeros(N).cuda()) if ln else None
+        ts = torch.zeros(64 * 1024, dtype=torch.int64, device="cuda")
+        for rep in range(3):
+            ts.zero_()
+            capi.lib().cotr_debug_set_timestamps(ctypes.c_void_p(ts.data_ptr()))
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            capi.test_gemm(0, A, W.numpy(), bias=bias, ln=ln_args)
+        capi.lib().cotr_debug_set_timestamps(None)
+        t = ts.cpu().view(-1, 64)
+        for cta in (0, 1):
+            r = t[cta].tolist()
+            print(f"  M={M} N={N} K={K} ln={ln} cta{cta}: setup {r[1]} fetch0 {r[2]} | loader got/pub " +
+                  " ".join(f"{r[3 + 2 * i]}/{r[4 + 2 * i]}" for i in range(min(8, (K + 63) // 64))) +
+                  f" | mma sawA/issued " + " ".join(f"{r[24 + 2 * i]}/{r[25 + 2 * i]}" for i in range(min(8, (K + 63) // 64))) +
+                  f" | tma " + " ".join(str(r[44 + i]) for i in range(min(8, (K + 63) // 64))) +
+                  f" | final commit {r[41]} acc ready {r[20]} epi done {r[21]} end {r[60]}", flush=True)
+
+
 def attn_cases(path):
     import torch
     from cotr_b200 import capi
@@ -192,6 +222,8 @@ def run_stage(name):
         model_case(0)
     elif name == "timing":
         timing()
+    elif name == "gemm_timeline":
+        gemm_timeline()
     elif name == "tc_precision":
         tc_precision()
     else:
