@@ -22,7 +22,7 @@ class CotrTensor(ctypes.Structure):
 class TestGemmDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "path", "M", "N", "K", "a_mode", "lda", "H", "W", "C", "OH", "OW", "KH", "KW", "stride", "pad",
-        "relu", "add_period", "ld_add", "ldr", "ldc")]
+        "relu", "add_period", "ld_add", "ldr", "ldc")] + [("a_elems", ctypes.c_int64)]
 
 
 class LaunchRecord(ctypes.Structure):
@@ -218,6 +218,7 @@ def test_gemm(path, A, w_host, *, bias=None, addmat=None, add_period=1, residual
         for k_, v_ in conv.items():
             setattr(d, k_, v_)
         d.lda = conv.get("C", 0) if a_mode != 3 else A.shape[-1]
+    d.a_elems = A.numel()
     d.relu = int(relu)
     d.add_period = add_period
     d.ld_add = addmat.stride(0) if addmat is not None else 0

@@ -1,12 +1,12 @@
 // Row/element addressing of the GEMM A operand (implicit im2col for the backbone convolutions).
 // Shared by the fp32 SIMT GEMM and the tcgen05 GEMM so both see exactly the same operand.
 #pragma once
-#include "common.cuh"
+#include "split16.cuh"
 
 namespace cotr {
 
 struct ARow {
-    const float* base;   // row start (row-major / token gather) or image base (convolutions)
+    size_t off;          // element offset of the row start (row-major / token gather) or of the image (convolutions)
     int ih0, iw0;        // convolutions: input coordinate of tap (0,0)
     bool valid;
 };
@@ -14,17 +14,17 @@ struct ARow {
 __device__ __forceinline__ ARow decode_a_row(const GemmParams& p, int m) {
     ARow r;
     r.valid = m < p.M;
-    r.base = p.A;
+    r.off = 0;
     r.ih0 = 0;
     r.iw0 = 0;
     if (!r.valid) return r;
     if (p.a_mode == A_ROWMAJOR) {
-        r.base = p.A + (size_t)m * p.lda;
+        r.off = (size_t)m * p.lda;
     } else if (p.a_mode == A_TOKENS) {
         // backbone.py:85 concatenates the two halves along W; transformer.py:50 flattens (i, j) -> i*32 + j
         const int pair = m >> 9, t = m & 511, i = t >> 5, j = t & 31;
         const int row = ((2 * pair + (j >> 4)) * 16 + i) * 16 + (j & 15);
-        r.base = p.A + (size_t)row * p.lda;
+        r.off = (size_t)row * p.lda;
     } else {
         const int ohw = p.OH * p.OW;
         const int n = m / ohw;
@@ -34,37 +34,36 @@ __device__ __forceinline__ ARow decode_a_row(const GemmParams& p, int m) {
         r.ih0 = oh * p.stride - p.pad;
         r.iw0 = ow * p.stride - p.pad;
         if (p.a_mode == A_CONV_NHWC) {
-            r.base = p.A + (size_t)n * p.H * p.W * p.C;
-        } else {  // A_STEM_NCHW: image n = 2*pair + half lives in columns [half*256, half*256+256) of the canvas
-            r.base = p.A + (size_t)(n >> 1) * 3 * 256 * 512 + (n & 1) * 256;
+            r.off = (size_t)n * p.H * p.W * p.C;
+        } else {  // A_STEM_NCHW: image n = 2*pair + half lives in columns [half*256, half*256+256) of the fp32 canvas
+            r.off = (size_t)(n >> 1) * 3 * 256 * 512 + (n & 1) * 256;
         }
     }
     return r;
 }
 
-// Elements k..k+3 of the row (k % 4 == 0); zero outside the matrix / in the convolution padding.
-__device__ __forceinline__ float4 load_a4(const GemmParams& p, const ARow& r, int k) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!r.valid || k >= p.K) return v;
-    if (p.a_mode == A_ROWMAJOR || p.a_mode == A_TOKENS) {
-        if (k + 3 < p.K && (p.lda & 3) == 0) {
-            v = __ldg(reinterpret_cast<const float4*>(r.base + k));
-        } else {
-            v.x = __ldg(r.base + k);
-            if (k + 1 < p.K) v.y = __ldg(r.base + k + 1);
-            if (k + 2 < p.K) v.z = __ldg(r.base + k + 2);
-            if (k + 3 < p.K) v.w = __ldg(r.base + k + 3);
-        }
-    } else if (p.a_mode == A_CONV_NHWC) {   // requires C % 4 == 0 so a float4 never straddles a tap
+// Element offset of (row, k) for the split16 modes with K % 8 == 0 (and C % 8 == 0): k..k+7 are contiguous.
+// Returns false for rows outside the matrix and for taps in the convolution padding.
+__device__ __forceinline__ bool a_offset8(const GemmParams& p, const ARow& r, int k, size_t& off) {
+    if (!r.valid || k >= p.K) return false;
+    if (p.a_mode == A_CONV_NHWC) {
         const int tap = k / p.C;
         const int c = k - tap * p.C;
         const int kh = tap / p.KW;
         const int kw = tap - kh * p.KW;
         const int ih = r.ih0 + kh, iw = r.iw0 + kw;
-        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
-            v = __ldg(reinterpret_cast<const float4*>(r.base + ((size_t)ih * p.W + iw) * p.C + c));
-    } else {                                // A_STEM_NCHW: K = 7*7*3, k -> (kh, kw, c), c fastest
-        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) return false;
+        off = r.off + ((size_t)ih * p.W + iw) * p.C + c;
+        return true;
+    }
+    off = r.off + k;
+    return true;
+}
+
+// fp32 stem: elements k..k+3 (k % 4 == 0) of the 7x7x3 patch; zero outside the half image / beyond K.
+__device__ __forceinline__ float4 load_stem4(const GemmParams& p, const ARow& r, int k) {
+    float e[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r.valid) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int kk = k + t;
@@ -75,12 +74,11 @@ __device__ __forceinline__ float4 load_a4(const GemmParams& p, const ARow& r, in
                 const int kw = tap - kh * 7;
                 const int ih = r.ih0 + kh, iw = r.iw0 + kw;
                 if (ih >= 0 && ih < 256 && iw >= 0 && iw < 256)
-                    e[t] = __ldg(r.base + (size_t)c * 256 * 512 + (size_t)ih * 512 + iw);
+                    e[t] = __ldg(p.a_f32 + r.off + (size_t)c * 256 * 512 + (size_t)ih * 512 + iw);
             }
         }
-        v = make_float4(e[0], e[1], e[2], e[3]);
     }
-    return v;
+    return make_float4(e[0], e[1], e[2], e[3]);
 }
 
 }  // namespace cotr

@@ -1,6 +1,7 @@
-// fp32 SIMT attention over the 512-token context: exact softmax(q k^T) v per head.
-// Numerical cross-check path for attention_tc.cu; also the fallback for launches with very few query rows.
-#include "common.cuh"
+// fp32 SIMT attention over the 512-token context on split16 operands: exact softmax(q k^T) v per head in plain fp32
+// arithmetic.  Numerical cross-check path for attention_tc.cu; also used for launches with very few query rows per
+// pair (the default engine's one-query-per-context step), where a 128-row MMA tile would be almost all padding.
+#include "split16.cuh"
 
 namespace cotr {
 
@@ -22,8 +23,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __global__ void __launch_bounds__(kWarps * 32) attention_simt_kernel(const AttnParams p) {
-    extern __shared__ __align__(16) float smem[];
-    float* Ks = smem;                                  // [512][33]
+    extern __shared__ __align__(16) float smem_f[];
+    float* Ks = smem_f;                                // [512][33]
     float* Vs = Ks + kTokens * kKStride;               // [512][32]
     float* Qs = Vs + kTokens * kHeadDim;               // [kWarps][32]
 
@@ -34,20 +35,27 @@ __global__ void __launch_bounds__(kWarps * 32) attention_simt_kernel(const AttnP
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
-    for (int idx = tid; idx < kTokens * (kHeadDim / 4); idx += blockDim.x) {
-        const int key = idx >> 3, d4 = (idx & 7) * 4;
-        const float4 kk = __ldg(reinterpret_cast<const float4*>(p.k + (kv_row0 + key) * p.ldk + head * kHeadDim + d4));
-        const float4 vv = __ldg(reinterpret_cast<const float4*>(p.v + (kv_row0 + key) * p.ldv + head * kHeadDim + d4));
-        float* kd = Ks + key * kKStride + d4;
-        kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
-        *reinterpret_cast<float4*>(Vs + key * kHeadDim + d4) = vv;
+    for (int idx = tid; idx < kTokens * (kHeadDim / 8); idx += blockDim.x) {        // K rows: 8 elements per step
+        const int key = idx >> 2, d8 = (idx & 3) * 8;
+        float v[8];
+        load8_split(p.k, (kv_row0 + key) * p.ldk + head * kHeadDim + d8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Ks[key * kKStride + d8 + j] = v[j];
+    }
+    const size_t vbase = (size_t)(p.pair0 + pair_local) * p.vt_pair_stride + (size_t)head * kHeadDim * kTokens;
+    for (int idx = tid; idx < kHeadDim * (kTokens / 8); idx += blockDim.x) {        // V^T rows: 8 keys per step
+        const int d = idx >> 6, k8 = (idx & 63) * 8;
+        float v[8];
+        load8_split(p.vt, vbase + (size_t)d * kTokens + k8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Vs[(k8 + j) * kHeadDim + d] = v[j];
     }
     __syncthreads();
 
     float* qs = Qs + warp * kHeadDim;
     for (int i = row_begin + warp; i < row_end; i += kWarps) {
         const size_t r = (size_t)pair_local * p.nq + i;
-        qs[lane] = __ldg(p.q + r * p.ldq + head * kHeadDim + lane);
+        qs[lane] = join_f16(p.q.hi[r * p.ldq + head * kHeadDim + lane], p.q.lo[r * p.ldq + head * kHeadDim + lane]);
         __syncwarp();
         float s[kTokens / 32];
 #pragma unroll
@@ -75,7 +83,10 @@ __global__ void __launch_bounds__(kWarps * 32) attention_simt_kernel(const AttnP
                 acc = fmaf(pj, Vs[(l + 32 * t) * kHeadDim + lane], acc);
             }
         }
-        p.out[r * p.ldo + head * kHeadDim + lane] = acc / sum;
+        __half h, lo;
+        split_f16(acc / sum, h, lo);
+        p.out.hi[r * p.ldo + head * kHeadDim + lane] = h;
+        p.out.lo[r * p.ldo + head * kHeadDim + lane] = lo;
         __syncwarp();
     }
 }

@@ -1,21 +1,21 @@
-// tcgen05 attention over the 512-token context (encoder self-attention and decoder cross-attention).
+// tcgen05 attention over the 512-token context (encoder self-attention and decoder cross-attention), split16 I/O.
 //
 // One CTA per (128-query tile, head, image pair).  The whole score tile S = Q K^T (128 x 512 fp32) fits TMEM exactly
 // (512 columns), so the softmax is exact (no online rescaling):
-//   warps 0-3  stage Q, K and V^T of this head as fp16 hi/lo core-matrix tiles (fp32-faithful 3-product scheme,
-//              see gemm_tc.cu), then run the softmax straight out of TMEM - each thread owns one query row, so the
-//              row max / row sum need no cross-thread reduction - and hand P to the MMA in 64-key chunks (double buffered);
+//   warps 0-3  stage Q, K and V^T of this head with asynchronous 16-byte copies (cp.async -> LDGSTS, completion on an
+//              mbarrier): the operands already live in HBM as fp16 hi/lo planes and V is stored transposed by the
+//              projection GEMM's epilogue, so staging is pure data movement into the UMMA canonical layout.  They then
+//              run the softmax straight out of TMEM - each thread owns one query row, so the row max / row sum need no
+//              cross-thread reduction - and hand P (split to fp16 hi/lo) to the MMA in 64-key chunks, double buffered;
 //   warp 4     (one lane) issues the tcgen05 MMAs: 2 x (128x256x32) for S, then 8 x (128x32x64) for O = P V.  The O
 //              accumulators re-use TMEM columns of S chunks that have already been turned into P: because the tensor
 //              core's fp32 accumulate truncates (profiles/r01_tc_precision.md) the hi*hi products alternate between
 //              two accumulators ([0,32) and [64,96)) and the small correction products go to a third ([32,64)).
 // q is expected pre-scaled by head_dim^-0.5 (folded into the projection weights).
-#include "common.cuh"
+#include "split16.cuh"
 #include "tc_common.cuh"
 
 namespace cotr {
-
-extern int g_tc_variant;
 
 namespace {
 
@@ -29,8 +29,8 @@ constexpr uint32_t kQLbo = kTile * 16;                    // Q tile  [4 K-groups
 constexpr uint32_t kQPlane = 4 * kQLbo;                   // 8 KB
 constexpr uint32_t kKLbo = kTokens * 16;                  // K tile  [4 K-groups][512 keys][16 B]
 constexpr uint32_t kKPlane = 4 * kKLbo;                   // 32 KB
-constexpr uint32_t kVLbo = kHeadDim * 16;                 // V^T tile [64 key-groups][32 d][16 B]
-constexpr uint32_t kVPlane = (kTokens / 8) * kVLbo;       // 32 KB
+constexpr uint32_t kVLbo = kHeadDim * 16 + 16;            // V^T tile [64 key-groups][32 d][16 B], padded against bank conflicts
+constexpr uint32_t kVPlane = (kTokens / 8) * kVLbo;       // 33 KB
 constexpr uint32_t kPLbo = kTile * 16;                    // P chunk [8 key-groups][128 rows][16 B]
 constexpr uint32_t kPPlane = (kChunk / 8) * kPLbo;        // 16 KB
 constexpr uint32_t kSbo = 128;
@@ -41,6 +41,7 @@ constexpr uint32_t kOffV = kOffK + 2 * kKPlane;
 constexpr uint32_t kOffP = kOffV + 2 * kVPlane;           // 2 buffers x (hi, lo)
 constexpr uint32_t kOffBar = kOffP + 4 * kPPlane;
 constexpr uint32_t kSmemBytes = kOffBar + 128;
+static_assert(kSmemBytes <= 227 * 1024, "attention tile does not fit shared memory");
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -48,11 +49,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-__device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t sbo, int variant) {
-    return (variant & 1) ? make_smem_desc(addr, sbo, lbo) : make_smem_desc(addr, lbo, sbo);
-}
-
-__global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnParams p, const int variant) {
+__global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint64_t* qk_full = bars + 0;
@@ -84,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t sbase = smem_u32(smem);
 
     if (warp < 4) {
         const int t = threadIdx.x;                       // == query row inside the tile == TMEM lane
@@ -92,70 +90,44 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         const size_t grow = (size_t)pair_local * p.nq + (row_ok ? qi : 0);
         const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
 
-        // ---- stage Q (one row per thread) and K (4 keys per thread) ------------------------------------------
+        // ---- stage Q (one row per thread) and K (4 keys per thread): 16-byte async copies ---------------------
         {
-            const float* src = p.q + grow * p.ldq + head * kHeadDim;
+            const size_t qoff = grow * p.ldq + head * kHeadDim;
+            const uint32_t bytes = row_ok ? 16u : 0u;
 #pragma unroll
             for (int kg = 0; kg < 4; ++kg) {
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (row_ok) {
-                    v0 = __ldg(reinterpret_cast<const float4*>(src + kg * 8));
-                    v1 = __ldg(reinterpret_cast<const float4*>(src + kg * 8 + 4));
-                }
-                uint4 hi, lo;
-                split_f16x2(v0.x, v0.y, hi.x, lo.x);
-                split_f16x2(v0.z, v0.w, hi.y, lo.y);
-                split_f16x2(v1.x, v1.y, hi.z, lo.z);
-                split_f16x2(v1.z, v1.w, hi.w, lo.w);
-                const uint32_t off = kg * kQLbo + t * 16;
-                *reinterpret_cast<uint4*>(smem + kOffQ + off) = hi;
-                *reinterpret_cast<uint4*>(smem + kOffQ + kQPlane + off) = lo;
+                const uint32_t dst = sbase + kOffQ + kg * kQLbo + t * 16;
+                cp_async16(dst, p.q.hi + qoff + kg * 8, bytes);
+                cp_async16(dst + kQPlane, p.q.lo + qoff + kg * 8, bytes);
             }
         }
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < kTokens / 128; ++i) {
             const int key = t + 128 * i;
-            const float* src = p.k + (kv_row0 + key) * p.ldk + head * kHeadDim;
+            const size_t koff = (kv_row0 + key) * p.ldk + head * kHeadDim;
 #pragma unroll
             for (int kg = 0; kg < 4; ++kg) {
-                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + kg * 8));
-                const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + kg * 8 + 4));
-                uint4 hi, lo;
-                split_f16x2(v0.x, v0.y, hi.x, lo.x);
-                split_f16x2(v0.z, v0.w, hi.y, lo.y);
-                split_f16x2(v1.x, v1.y, hi.z, lo.z);
-                split_f16x2(v1.z, v1.w, hi.w, lo.w);
-                const uint32_t off = kg * kKLbo + key * 16;
-                *reinterpret_cast<uint4*>(smem + kOffK + off) = hi;
-                *reinterpret_cast<uint4*>(smem + kOffK + kKPlane + off) = lo;
+                const uint32_t dst = sbase + kOffK + kg * kKLbo + key * 16;
+                cp_async16(dst, p.k.hi + koff + kg * 8, 16u);
+                cp_async16(dst + kKPlane, p.k.lo + koff + kg * 8, 16u);
             }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(qk_full);
+        cp_async_mbar_arrive_noinc(qk_full);
 
-        // ---- stage V^T: B operand of O = P V is [d][key] with keys contiguous (K-major) ------------------------
-#pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-            const int u = t + 128 * i;
-            const int dq = u & 7, kg8 = u >> 3;
-            const float* src = p.v + (kv_row0 + (size_t)kg8 * 8) * p.ldv + head * kHeadDim + dq;
+        // ---- stage V^T (already transposed in HBM): piece (key-group kg8, d) = 8 consecutive keys of row d ----
+        {
+            const size_t vbase = (size_t)(p.pair0 + pair_local) * p.vt_pair_stride + (size_t)head * kHeadDim * kTokens;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float x[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = __ldg(src + (size_t)j * p.ldv + 8 * e);
-                uint4 hi, lo;
-                split_f16x2(x[0], x[1], hi.x, lo.x);
-                split_f16x2(x[2], x[3], hi.y, lo.y);
-                split_f16x2(x[4], x[5], hi.z, lo.z);
-                split_f16x2(x[6], x[7], hi.w, lo.w);
-                const uint32_t off = kg8 * kVLbo + (dq + 8 * e) * 16;
-                *reinterpret_cast<uint4*>(smem + kOffV + off) = hi;
-                *reinterpret_cast<uint4*>(smem + kOffV + kVPlane + off) = lo;
+            for (int i = 0; i < 16; ++i) {
+                const int u = t + 128 * i;
+                const int kg8 = u & 63, d = u >> 6;
+                const uint32_t dst = sbase + kOffV + kg8 * kVLbo + d * 16;
+                const size_t voff = vbase + (size_t)d * kTokens + kg8 * 8;
+                cp_async16(dst, p.vt.hi + voff, 16u);
+                cp_async16(dst + kVPlane, p.vt.lo + voff, 16u);
             }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(v_full);
+        cp_async_mbar_arrive_noinc(v_full);
 
         // ---- softmax out of TMEM ---------------------------------------------------------------------------
         mbar_wait(s_full, 0);
@@ -163,12 +135,17 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < kTokens; c += 16) {
-            float v[16];
+        for (int c = 0; c < kTokens; c += 64) {
+            uint32_t r[4][16];
             __syncwarp();
-            tmem_ld16(trow + c, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
+            for (int h = 0; h < 4; ++h) tmem_ld16_issue(trow + c + h * 16, r[h]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) tmem_ld16_fence(r[h]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[h][j]));
         }
         const float kLog2e = 1.4426950408889634f;
         const float mxs = mx * kLog2e;
@@ -176,17 +153,21 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c) {
             const int buf = c & 1;
+            uint32_t r[4][16];
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 4; ++h) tmem_ld16_issue(trow + c * kChunk + h * 16, r[h]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) tmem_ld16_fence(r[h]);
             if (c >= 2) mbar_wait(&p_empty[buf], (uint32_t)((c >> 1) - 1) & 1u);
-            uint8_t* p_hi = smem + kOffP + buf * 2 * kPPlane;
+            uint8_t* p_hi = smem + kOffP + buf * 2 * kPPlane + t * 16;
             uint8_t* p_lo = p_hi + kPPlane;
 #pragma unroll
-            for (int h = 0; h < kChunk / 16; ++h) {
+            for (int h = 0; h < 4; ++h) {
                 float v[16];
-                __syncwarp();
-                tmem_ld16(trow + c * kChunk + h * 16, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    v[j] = fast_exp2(fmaf(v[j], kLog2e, -mxs));
+                    v[j] = fast_exp2(fmaf(__uint_as_float(r[h][j]), kLog2e, -mxs));
                     sum += v[j];
                 }
 #pragma unroll
@@ -196,9 +177,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                     split_f16x2(v[g * 8 + 2], v[g * 8 + 3], hi.y, lo.y);
                     split_f16x2(v[g * 8 + 4], v[g * 8 + 5], hi.z, lo.z);
                     split_f16x2(v[g * 8 + 6], v[g * 8 + 7], hi.w, lo.w);
-                    const uint32_t off = (h * 2 + g) * kPLbo + t * 16;
-                    *reinterpret_cast<uint4*>(p_hi + off) = hi;
-                    *reinterpret_cast<uint4*>(p_lo + off) = lo;
+                    *reinterpret_cast<uint4*>(p_hi + (h * 2 + g) * kPLbo) = hi;
+                    *reinterpret_cast<uint4*>(p_lo + (h * 2 + g) * kPLbo) = lo;
                 }
             }
             tcgen05_fence_before();
@@ -206,32 +186,36 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
             mbar_arrive(&p_full[buf]);
         }
 
-        // ---- O / sum -> global -----------------------------------------------------------------------------
+        // ---- O / sum -> global (split16) ---------------------------------------------------------------------
         mbar_wait(o_full, 0);
         tcgen05_fence_after();
         const float inv = 1.f / sum;
-        float* dst = p.out + grow * p.ldo + head * kHeadDim;
+        const size_t ooff = grow * p.ldo + head * kHeadDim;
 #pragma unroll
         for (int c = 0; c < kHeadDim; c += 16) {
-            float v[16], w1[16], w2[16];
+            uint32_t r0[16], r1[16], r2[16];
             __syncwarp();
-            tmem_ld16(trow + c, v);
-            tmem_ld16(trow + 64 + c, w1);
-            tmem_ld16(trow + 32 + c, w2);
+            tmem_ld16_issue(trow + c, r0);
+            tmem_ld16_issue(trow + 64 + c, r1);
+            tmem_ld16_issue(trow + 32 + c, r2);
+            tmem_ld16_fence(r0);
+            tmem_ld16_fence(r1);
+            tmem_ld16_fence(r2);
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (v[j] + w1[j]) + w2[j];
+            for (int j = 0; j < 16; ++j)
+                v[j] = ((__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j])) * inv;
             if (row_ok) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(dst + c + j) = make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv);
+                store8_split(p.out, ooff + c, v);
+                store8_split(p.out, ooff + c + 8, v + 8);
             }
         }
     } else {
         // ================= MMA issuer =========================================================================
         if (lane == 0) {
-            const uint32_t sbase = smem_u32(smem);
             constexpr uint32_t idesc_s = make_idesc_f16_f32(128, 256);
             constexpr uint32_t idesc_o = make_idesc_f16_f32(128, kHeadDim);
+            const uint32_t hi_word = desc_hi(kSbo);
             mbar_wait(qk_full, 0);
             tcgen05_fence_after();
 #pragma unroll
@@ -240,8 +224,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                 for (int ks = 0; ks < 2; ++ks) {
                     const uint32_t qa = sbase + kOffQ + ks * 2 * kQLbo;
                     const uint32_t ka = sbase + kOffK + nh * 256 * 16 + ks * 2 * kKLbo;
-                    const uint64_t qh = desc(qa, kQLbo, kSbo, variant), ql = desc(qa + kQPlane, kQLbo, kSbo, variant);
-                    const uint64_t kh = desc(ka, kKLbo, kSbo, variant), kl = desc(ka + kKPlane, kKLbo, kSbo, variant);
+                    const uint64_t qh = make_desc(desc_lo(qa, kQLbo), hi_word), ql = make_desc(desc_lo(qa + kQPlane, kQLbo), hi_word);
+                    const uint64_t kh = make_desc(desc_lo(ka, kKLbo), hi_word), kl = make_desc(desc_lo(ka + kKPlane, kKLbo), hi_word);
                     const uint32_t d = tmem_base + nh * 256;
                     umma_f16_ss(d, ql, kh, idesc_s, ks != 0);
                     umma_f16_ss(d, qh, kl, idesc_s, true);
@@ -255,14 +239,14 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                 const int buf = c & 1;
                 mbar_wait(&p_full[buf], (uint32_t)(c >> 1) & 1u);
                 tcgen05_fence_after();
+                // chunk c may only touch TMEM columns of S chunks <= c (already consumed by the softmax warps)
+                const uint32_t o_main = tmem_base + ((c & 1) ? 64u : 0u);
 #pragma unroll
                 for (int ks = 0; ks < kChunk / 16; ++ks) {
                     const uint32_t pa = sbase + kOffP + buf * 2 * kPPlane + ks * 2 * kPLbo;
                     const uint32_t va = sbase + kOffV + (c * (kChunk / 8) + ks * 2) * kVLbo;
-                    const uint64_t ph = desc(pa, kPLbo, kSbo, variant), pl = desc(pa + kPPlane, kPLbo, kSbo, variant);
-                    const uint64_t vh = desc(va, kVLbo, kSbo, variant), vl = desc(va + kVPlane, kVLbo, kSbo, variant);
-                    // chunk c may only touch TMEM columns of S chunks <= c (already consumed by the softmax warps)
-                    const uint32_t o_main = tmem_base + ((c & 1) ? 64u : 0u);
+                    const uint64_t ph = make_desc(desc_lo(pa, kPLbo), hi_word), pl = make_desc(desc_lo(pa + kPPlane, kPLbo), hi_word);
+                    const uint64_t vh = make_desc(desc_lo(va, kVLbo), hi_word), vl = make_desc(desc_lo(va + kVPlane, kVLbo), hi_word);
                     umma_f16_ss(tmem_base + 32u, pl, vh, idesc_o, (c | ks) != 0);
                     umma_f16_ss(tmem_base + 32u, ph, vl, idesc_o, true);
                     umma_f16_ss(o_main, ph, vh, idesc_o, (c >= 2) || ks != 0);
@@ -290,9 +274,10 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
         configured = true;
     }
     COTR_CHECK(p.npairs <= 65535, "attention: too many pairs in one launch (%d)", p.npairs);
-    COTR_CHECK((p.ldq & 3) == 0 && (p.ldk & 3) == 0 && (p.ldo & 3) == 0, "attention_tc: leading dimensions must be multiples of 4");
+    COTR_CHECK((p.ldq & 7) == 0 && (p.ldk & 7) == 0 && (p.ldo & 7) == 0 && (p.vt_pair_stride & 7) == 0,
+               "attention_tc: leading dimensions must be multiples of 8 elements");
     dim3 grid((p.nq + kTile - 1) / kTile, kHeads, p.npairs);
-    attention_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, g_tc_variant);
+    attention_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
     COTR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,5 +1,6 @@
 // Shared declarations of the cotr_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdint>
@@ -34,63 +35,94 @@ constexpr int kFF = 1024;
 constexpr int kEncLayers = 6;
 constexpr int kDecLayers = 6;
 
+// ---------------------------------------------------------------------------------------------------------------
+// "split16" activations.  Every activation between kernels is stored as TWO fp16 planes, x ~= hi + lo (22 mantissa
+// bits, same bytes as fp32): the tensor-core kernels need their operands in exactly that form (gemm_tc.cu), so the
+// producer's epilogue splits once and every consumer stages its operand with plain asynchronous 16-byte copies.
+// hi + lo is exactly representable in fp32, so reconstruct -> split round-trips are lossless.
+// ---------------------------------------------------------------------------------------------------------------
+struct Split16 {          // plain aggregates: they travel inside kernel parameter structs
+    __half* hi;
+    __half* lo;
+};
+struct CSplit16 {
+    const __half* hi;
+    const __half* lo;
+};
+inline CSplit16 cs(const Split16& s) { return CSplit16{s.hi, s.lo}; }
+inline Split16 offset(const Split16& s, size_t elems) { return Split16{s.hi + elems, s.lo + elems}; }
+inline CSplit16 offset(const CSplit16& s, size_t elems) { return CSplit16{s.hi + elems, s.lo + elems}; }
+
 // How a GEMM finds row m, column k of its A operand.
 enum AMode : int {
     A_ROWMAJOR = 0,   // A[m * lda + k]
     A_CONV_NHWC = 1,  // implicit im2col over an NHWC activation: m -> (n, oh, ow), k -> (kh, kw, c)
-    A_STEM_NCHW = 2,  // implicit im2col over the (B,3,256,512) NCHW canvas, halves as separate images
+    A_STEM_NCHW = 2,  // implicit im2col over the fp32 (B,3,256,512) NCHW canvas, halves as separate images
     A_TOKENS = 3,     // m = pair*512 + i*32 + j gathers row ((2*pair + (j>>4))*16 + i)*16 + (j&15)
 };
 
-// D[M,N] = epilogue( A[M,K] * W[N,K]^T ).  Everything fp32 in global memory.
+// D[M,N] = epilogue( A[M,K] * W[N,K]^T ).
 struct GemmParams {
     int M, N, K;
-    const float* A;
+    // A operand: split16 activation, or the fp32 input canvas for A_STEM_NCHW
+    CSplit16 a;
+    const float* a_f32;
     int a_mode;
     int lda;
-    // conv geometry (A_CONV_NHWC / A_STEM_NCHW)
-    int H, W, C;      // input height / width / channels (per image)
+    int H, W, C;      // convolution geometry: input height / width / channels (per image)
     int OH, OW;       // output height / width
     int KH, KW, stride, pad;
-    // weights, row-major [N, K] (K ordered (kh, kw, c) for convolutions)
+    // weights: fp32 row-major [N, K] (K ordered (kh, kw, c) for convolutions) for the SIMT path; for the tensor-core
+    // path the same matrix pre-scaled by a power of two, pre-split into fp16 hi/lo and pre-tiled (gemm_tc.cu).
     const float* Wt;
-    // tensor-core path: the same weights pre-scaled by a power of two, pre-split into fp16 hi/lo and pre-tiled
-    // (see gemm_tc.cu); may be null.  acc_scale undoes the power of two on the accumulator.
     const void* Wtc;
-    float acc_scale;
-    // epilogue: v = acc + bias[n] + addmat[(m % add_period) * ld_add + n] + residual[m * ldr + n]; relu; LN
+    float acc_scale;  // undoes the power of two on the accumulator
+    // epilogue: v = acc * acc_scale + bias[n] + addmat[(m % add_period) * ld_add + n] + residual[m * ldr + n]; relu; LN
     const float* bias;
     const float* addmat;
     int add_period, ld_add;
-    const float* residual;
+    CSplit16 res;
     int ldr;
     int relu;
-    // optional fused LayerNorm over the N = 256 columns of each row (after residual), tensor-core path only
-    const float* ln_gamma;
+    const float* ln_gamma;   // optional LayerNorm over the N = 256 columns of each row (after the residual)
     const float* ln_beta;
-    float* out;
+    // outputs
+    float* out_f32;          // when non-null: plain fp32 row-major output (the final prediction, N = 2)
+    Split16 out;             // otherwise split16, row-major with leading dimension ldc ...
     int ldc;
+    // ... except that 256-column blocks of N can be redirected (K/V projections): blk_map[b] >= 0 -> the block is
+    // stored at column offset blk_map[b] of `out`; blk_map[b] = -(v+1) -> the block is a value projection and is
+    // stored TRANSPOSED as vt[((pair * n_vt + v) * 256 + c) * 512 + key] (row = pair*512 + key), the K-major B operand
+    // the attention kernels need.
+    int remap;
+    int blk_map[12];
+    Split16 vt;
+    int n_vt;
 };
 
 // softmax(q k^T) v per head; q already carries the head_dim^-0.5 scale.
 struct AttnParams {
-    const float* q; int ldq;     // rows: local row r = pair_local * nq + i
-    const float* k; int ldk;     // rows: (pair0 + pair_local) * 512 + key
-    const float* v; int ldv;
-    float* out; int ldo;
+    CSplit16 q; int ldq;         // rows: local row r = pair_local * nq + i
+    CSplit16 k; int ldk;         // rows: (pair0 + pair_local) * 512 + key
+    CSplit16 vt;                 // [(pair0 + pair_local) * vt_pair_stride + (head*32 + d) * 512 + key]
+    size_t vt_pair_stride;
+    Split16 out; int ldo;
     int nq;                      // query rows per pair in this launch
     int npairs;
     int pair0;
 };
 
 int launch_gemm_simt(const GemmParams& p, cudaStream_t s);
+int launch_gemm_simt_raw(const GemmParams& p, float* raw_out_f32, cudaStream_t s);   // result as plain fp32 [M,N]
+int launch_layernorm_f32(const float* x, const float* gamma, const float* beta, Split16 out, int rows, cudaStream_t s);
 int launch_gemm_tc(const GemmParams& p, cudaStream_t s);
 int launch_attention_simt(const AttnParams& p, cudaStream_t s);
 int launch_attention_tc(const AttnParams& p, cudaStream_t s);
-int launch_maxpool_3x3s2_nhwc(const float* in, float* out, int N, int H, int W, int C, cudaStream_t s);
-int launch_layernorm(const float* x, const float* residual, const float* gamma, const float* beta, float* out,
-                     int rows, cudaStream_t s);
-int launch_query_encode(const float* queries, float* qpos, int rows, cudaStream_t s);
+int launch_maxpool_3x3s2_nhwc(CSplit16 in, Split16 out, int N, int H, int W, int C, cudaStream_t s);
+int launch_layernorm(CSplit16 x, const float* gamma, const float* beta, Split16 out, int rows, cudaStream_t s);
+int launch_query_encode(const float* queries, Split16 qpos, int rows, cudaStream_t s);
+int launch_f32_to_split16(const float* in, Split16 out, size_t n, cudaStream_t s);
+int launch_split16_to_f32(CSplit16 in, float* out, size_t n, cudaStream_t s);
 
 // Bytes of the pre-tiled fp16 hi/lo image of an [N,K] weight matrix, and the host-side packer (returns acc_scale).
 size_t tc_weight_bytes(int N, int K);

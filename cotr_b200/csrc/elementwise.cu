@@ -1,23 +1,25 @@
-// Small HBM-bound kernels of the hot path: stem max-pool, LayerNorm, lin_sine query encoding.
-#include "common.cuh"
+// Small HBM-bound kernels of the hot path on split16 activations: stem max-pool, LayerNorm, lin_sine query encoding,
+// and the fp32 <-> split16 converters used at the boundary (test hooks, debug reads, constant tables).
+#include "split16.cuh"
 
 namespace cotr {
 
 namespace {
 
-// torchvision resnet stem: MaxPool2d(kernel 3, stride 2, padding 1) on NHWC, float4 over channels.
-__global__ void maxpool_3x3s2_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                          int N, int H, int W, int C4) {
+// torchvision resnet stem: MaxPool2d(kernel 3, stride 2, padding 1) on NHWC, 8 channels per thread.
+__global__ void maxpool_3x3s2_nhwc_kernel(const CSplit16 in, const Split16 out, int N, int H, int W, int C8) {
     const int OH = H / 2, OW = W / 2;
-    const size_t total = (size_t)N * OH * OW * C4;
+    const size_t total = (size_t)N * OH * OW * C8;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = idx % C4;
-        size_t t = idx / C4;
+        const int c8 = idx % C8;
+        size_t t = idx / C8;
         const int ow = t % OW; t /= OW;
         const int oh = t % OH;
         const int n = t / OH;
-        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
 #pragma unroll
         for (int dh = 0; dh < 3; ++dh) {
             const int ih = oh * 2 - 1 + dh;
@@ -26,11 +28,13 @@ __global__ void maxpool_3x3s2_nhwc_kernel(const float* __restrict__ in, float* _
             for (int dw = 0; dw < 3; ++dw) {
                 const int iw = ow * 2 - 1 + dw;
                 if (iw < 0 || iw >= W) continue;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(in) + (((size_t)n * H + ih) * W + iw) * C4 + c4);
-                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                float v[8];
+                load8_split(in, ((((size_t)n * H + ih) * W + iw) * C8 + c8) * 8, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
             }
         }
-        reinterpret_cast<float4*>(out)[idx] = m;
+        store8_split(out, idx * 8, m);      // hi + lo is exact in fp32, so the re-split is lossless
     }
 }
 
@@ -40,40 +44,43 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// out = LayerNorm(x (+ residual)) over 256 channels, eps 1e-5, biased variance.  One warp per row.
-__global__ void __launch_bounds__(256) layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ residual,
+// out = LayerNorm(x) over 256 channels, eps 1e-5, biased variance.  One warp per row, 8 channels per lane.
+template <bool F32_IN>
+__global__ void __launch_bounds__(256) layernorm256_kernel(const CSplit16 x, const float* __restrict__ x_f32,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           float* __restrict__ out, int rows) {
+                                                           const Split16 out, int rows) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * kDModel);
-    float4 a = xr[lane], b = xr[32 + lane];
-    if (residual) {
-        const float4* rr = reinterpret_cast<const float4*>(residual + (size_t)warp * kDModel);
-        const float4 ra = rr[lane], rb = rr[32 + lane];
-        a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
-        b.x += rb.x; b.y += rb.y; b.z += rb.z; b.w += rb.w;
+    const size_t off = (size_t)warp * kDModel + lane * 8;
+    float v[8];
+    if constexpr (F32_IN) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x_f32 + off));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x_f32 + off + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        load8_split(x, off, v);
     }
-    const float mean = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / kDModel);
-    a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
-    b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
-    const float var = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w +
-                               b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w) * (1.f / kDModel);
-    const float rstd = 1.f / sqrtf(var + 1e-5f);
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
-    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta) + lane), bb = __ldg(reinterpret_cast<const float4*>(beta) + 32 + lane);
-    float4 oa, ob;
-    oa.x = a.x * rstd * ga.x + ba.x; oa.y = a.y * rstd * ga.y + ba.y; oa.z = a.z * rstd * ga.z + ba.z; oa.w = a.w * rstd * ga.w + ba.w;
-    ob.x = b.x * rstd * gb.x + bb.x; ob.y = b.y * rstd * gb.y + bb.y; ob.z = b.z * rstd * gb.z + bb.z; ob.w = b.w * rstd * gb.w + bb.w;
-    float4* orow = reinterpret_cast<float4*>(out + (size_t)warp * kDModel);
-    orow[lane] = oa;
-    orow[32 + lane] = ob;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    const float mean = warp_sum(s) * (1.f / kDModel);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] -= mean; sq = fmaf(v[j], v[j], sq); }
+    const float rstd = 1.f / sqrtf(warp_sum(sq) * (1.f / kDModel) + 1e-5f);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + lane * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + lane * 8 + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * rstd * g[j] + b[j];
+    store8_split(out, off, v);
 }
 
 // position_encoding.py:41-45 with bases 1..64 on (x, y):
 // channel 2(k-1)+a = sin(fp32(k*pi) * p_a), channel 128 + 2(k-1)+a = cos(...).  Accurate sincosf: |angle| <= 64*pi.
-__global__ void __launch_bounds__(128) query_encode_kernel(const float* __restrict__ queries, float* __restrict__ qpos, int rows) {
+__global__ void __launch_bounds__(128) query_encode_kernel(const float* __restrict__ queries, const Split16 qpos, int rows) {
     const int row = blockIdx.x;
     if (row >= rows) return;
     const int t = threadIdx.x;          // 0..127 = 2*(k-1) + axis
@@ -83,33 +90,74 @@ __global__ void __launch_bounds__(128) query_encode_kernel(const float* __restri
     const float angle = __fmul_rn(kpi, p);
     float s, c;
     sincosf(angle, &s, &c);
-    qpos[(size_t)row * kDModel + t] = s;
-    qpos[(size_t)row * kDModel + 128 + t] = c;
+    __half h, l;
+    split_f16(s, h, l);
+    qpos.hi[(size_t)row * kDModel + t] = h;
+    qpos.lo[(size_t)row * kDModel + t] = l;
+    split_f16(c, h, l);
+    qpos.hi[(size_t)row * kDModel + 128 + t] = h;
+    qpos.lo[(size_t)row * kDModel + 128 + t] = l;
+}
+
+__global__ void f32_to_split16_kernel(const float* __restrict__ in, const Split16 out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        __half h, l;
+        split_f16(in[i], h, l);
+        out.hi[i] = h;
+        out.lo[i] = l;
+    }
+}
+__global__ void split16_to_f32_kernel(const CSplit16 in, float* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = join_f16(in.hi[i], in.lo[i]);
+}
+
+int grid_for(size_t total, int block) {
+    const size_t blocks = (total + block - 1) / block;
+    return (int)(blocks < 148 * 16 ? (blocks ? blocks : 1) : 148 * 16);
 }
 
 }  // namespace
 
-int launch_maxpool_3x3s2_nhwc(const float* in, float* out, int N, int H, int W, int C, cudaStream_t s) {
-    COTR_CHECK((C & 3) == 0 && (H & 1) == 0 && (W & 1) == 0, "maxpool: unsupported shape");
-    const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 4);
-    const int block = 256;
-    const int grid = (int)((total + block - 1) / block < 148 * 16 ? (total + block - 1) / block : 148 * 16);
-    maxpool_3x3s2_nhwc_kernel<<<grid, block, 0, s>>>(in, out, N, H, W, C / 4);
+int launch_maxpool_3x3s2_nhwc(CSplit16 in, Split16 out, int N, int H, int W, int C, cudaStream_t s) {
+    COTR_CHECK((C & 7) == 0 && (H & 1) == 0 && (W & 1) == 0, "maxpool: unsupported shape");
+    const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
+    maxpool_3x3s2_nhwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, N, H, W, C / 8);
     COTR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_layernorm(const float* x, const float* residual, const float* gamma, const float* beta, float* out,
-                     int rows, cudaStream_t s) {
+int launch_layernorm(CSplit16 x, const float* gamma, const float* beta, Split16 out, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
-    layernorm256_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, residual, gamma, beta, out, rows);
+    layernorm256_kernel<false><<<(rows + 7) / 8, 256, 0, s>>>(x, nullptr, gamma, beta, out, rows);
     COTR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_query_encode(const float* queries, float* qpos, int rows, cudaStream_t s) {
+int launch_layernorm_f32(const float* x, const float* gamma, const float* beta, Split16 out, int rows, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    layernorm256_kernel<true><<<(rows + 7) / 8, 256, 0, s>>>(CSplit16{nullptr, nullptr}, x, gamma, beta, out, rows);
+    COTR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_query_encode(const float* queries, Split16 qpos, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
     query_encode_kernel<<<rows, 128, 0, s>>>(queries, qpos, rows);
+    COTR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_f32_to_split16(const float* in, Split16 out, size_t n, cudaStream_t s) {
+    if (n == 0) return 0;
+    f32_to_split16_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n);
+    COTR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_split16_to_f32(CSplit16 in, float* out, size_t n, cudaStream_t s) {
+    if (n == 0) return 0;
+    split16_to_f32_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n);
     COTR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

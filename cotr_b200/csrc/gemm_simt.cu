@@ -1,6 +1,6 @@
-// fp32 SIMT GEMM with implicit-im2col A loader and fused epilogue.
-// Numerical cross-check path (cotr_set_gemm_path(m, 1)) and the producer of the constant
-// position-bias matrices at model creation.  The product path is gemm_tc.cu (tcgen05).
+// fp32 SIMT GEMM on split16 activations with the same implicit-im2col A addressing and the same epilogue contract as
+// the tcgen05 GEMM.  Numerical cross-check path (cotr_set_gemm_path(m, 1): plain fp32 FMA arithmetic on the
+// reconstructed hi + lo values) and the producer of the constant position-bias matrices at model creation.
 #include "a_loader.cuh"
 
 namespace cotr {
@@ -9,7 +9,20 @@ namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
 
-__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
+// A[m, k..k+3] as fp32 (k % 4 == 0)
+__device__ __forceinline__ float4 load_a4_f32(const GemmParams& p, const ARow& r, int k) {
+    if (p.a_mode == A_STEM_NCHW) return load_stem4(p, r, k);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    size_t off;
+    if (!a_offset8(p, r, k & ~7, off)) return v;     // all split16 operands have K % 8 == 0
+    off += (k & 4);
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(p.a.hi + off));
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(p.a.lo + off));
+    const float2 a = join_f16x2(h.x, l.x), b = join_f16x2(h.y, l.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p, float* __restrict__ raw_out) {
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
 
@@ -33,7 +46,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
 
     for (int k0 = 0; k0 < p.K; k0 += BK) {
         const int k = k0 + lk;
-        const float4 a = load_a4(p, arow, k);
+        const float4 a = load_a4_f32(p, arow, k);
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (wn < p.N && k < p.K) {
             if (w_vec) {
@@ -67,7 +80,6 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
         const int m = m0 + ty * 4 + i;
         if (m >= p.M) continue;
         const float* add_row = p.addmat ? p.addmat + (size_t)(m % p.add_period) * p.ld_add : nullptr;
-        const float* res_row = p.residual ? p.residual + (size_t)m * p.ldr : nullptr;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
@@ -75,23 +87,40 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
             float v = acc[i][j];
             if (p.bias) v += __ldg(p.bias + n);
             if (add_row) v += __ldg(add_row + n);
-            if (res_row) v += __ldg(res_row + n);
+            if (p.res.hi) v += join_f16(p.res.hi[(size_t)m * p.ldr + n], p.res.lo[(size_t)m * p.ldr + n]);
             if (p.relu) v = fmaxf(v, 0.f);
-            p.out[(size_t)m * p.ldc + n] = v;
+            if (raw_out) {                       // fp32 scratch (pre-LayerNorm rows, or a constant add-matrix)
+                raw_out[(size_t)m * p.N + n] = v;
+            } else if (p.out_f32) {
+                p.out_f32[(size_t)m * p.ldc + n] = v;
+            } else {
+                size_t base;
+                const bool transposed = out_location(p, m, n & ~15, base);
+                const size_t idx = transposed ? base + (size_t)(n & 15) * kTokens : base + (n & 15);
+                __half h, l;
+                split_f16(v, h, l);
+                if (transposed) { p.vt.hi[idx] = h; p.vt.lo[idx] = l; }
+                else { p.out.hi[idx] = h; p.out.lo[idx] = l; }
+            }
         }
     }
 }
 
 }  // namespace
 
-int launch_gemm_simt(const GemmParams& p, cudaStream_t s) {
+// raw_out != nullptr: write the epilogue result as plain fp32 [M, N] there instead of p.out (used for the constant
+// add-matrices and as the LayerNorm staging buffer of the SIMT path).
+int launch_gemm_simt_raw(const GemmParams& p, float* raw_out, cudaStream_t s) {
     COTR_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "gemm_simt: empty problem %d x %d x %d", p.M, p.N, p.K);
-    COTR_CHECK(p.a_mode != A_CONV_NHWC || (p.C & 3) == 0, "gemm_simt: NHWC conv needs C %% 4 == 0 (C=%d)", p.C);
+    COTR_CHECK(p.a_mode == A_STEM_NCHW || (p.K & 7) == 0, "gemm_simt: split16 operands need K %% 8 == 0 (K=%d)", p.K);
+    COTR_CHECK(p.a_mode != A_CONV_NHWC || (p.C & 7) == 0, "gemm_simt: NHWC conv needs C %% 8 == 0 (C=%d)", p.C);
     COTR_CHECK(p.ln_gamma == nullptr, "gemm_simt: fused LayerNorm is a tensor-core-path feature");
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-    gemm_simt_kernel<<<grid, 256, 0, s>>>(p);
+    gemm_simt_kernel<<<grid, 256, 0, s>>>(p, raw_out);
     COTR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+int launch_gemm_simt(const GemmParams& p, cudaStream_t s) { return launch_gemm_simt_raw(p, nullptr, s); }
 
 }  // namespace cotr

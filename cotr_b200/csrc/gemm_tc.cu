@@ -1,24 +1,26 @@
-// tcgen05 GEMM for sm_100a:  D[M,N] = epilogue( A[M,K] * W[N,K]^T ),  fp32 in / fp32 out.
+// tcgen05 GEMM for sm_100a:  D[M,N] = epilogue( A[M,K] * W[N,K]^T ) on split16 activations (common.cuh).
 //
 // Precision: the 1e-3 parity bar on predicted (x,y) rules out single-pass bf16 / tf32 / fp16 operands
-// (SURVEY.md appendix E.3).  Each fp32 operand is split into two fp16 terms (x ~= hi + lo, ~22 mantissa bits)
-// and the product is formed as  hi*hi + hi*lo + lo*hi  with fp32 accumulation in TMEM - three kind::f16 MMAs
-// per K step.  Weights are pre-multiplied by a per-tensor power of two so that their lo terms stay in fp16's
-// normal range; the epilogue multiplies the accumulator by the inverse (exact).  The tensor core adds into its fp32
-// accumulator with truncation (measured: ~1e-7 relative per chained MMA, profiles/r01_tc_precision.md), so the K steps
-// are dealt round-robin onto several TMEM accumulators and the small hi*lo / lo*hi products onto a separate one; the
-// epilogue adds them up with fp32 round-to-nearest.
+// (SURVEY.md appendix E.3).  Every operand is a pair of fp16 values (x ~= hi + lo, ~22 mantissa bits) and a product
+// is formed as  hi*hi + hi*lo + lo*hi  with fp32 accumulation in TMEM - three kind::f16 MMAs per K step.  Weights are
+// pre-multiplied by a per-tensor power of two so that their lo terms stay in fp16's normal range; the epilogue
+// multiplies the accumulator by the inverse (exact).  The tensor core adds into its fp32 accumulator with truncation
+// (measured: ~1e-7 relative per chained MMA, profiles/r01_tc_precision.md), so the K steps are dealt round-robin onto
+// several TMEM accumulators and the small hi*lo / lo*hi products onto a separate one; the epilogue adds them up with
+// fp32 round-to-nearest.
 //
 // Data movement per CTA (one 128 x BN output tile, K walked in chunks of 64):
 //   * weights: pre-split, pre-tiled in HBM at model creation (tc_pack_weight) into 64-row x 64-k blocks that ARE the
 //     UMMA canonical shared-memory image, so a pipeline stage is BN/64 contiguous 16 KB bulk-TMA copies
 //     (cp.async.bulk -> UBLKCP) completing on an mbarrier;
-//   * activations: warps 0-3 load fp32 (implicit im2col for the convolutions), split to fp16 hi/lo in registers
-//     (loads for chunk i+1 are in flight while chunk i is converted) and store 16-byte core-matrix rows to shared
-//     memory (conflict-free thanks to a padded LBO);
+//   * activations: already split16 in HBM (the producer's epilogue split them), so warps 0-3 stage the A tile with
+//     asynchronous 16-byte copies (cp.async -> LDGSTS, zero-filled for im2col padding / row tails) whose completion
+//     arrives on the stage's mbarrier (cp.async.mbarrier.arrive.noinc) - no registers, no conversion, up to kStages
+//     chunks in flight.  Only the 7x7 stem reads the caller's fp32 canvas and converts in registers;
 //   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma (N = 64 atoms) and owns TMEM;
 //   * warps 0-3 then run the epilogue out of TMEM: bias / constant add-matrix / residual / ReLU, or the fused
-//     residual + LayerNorm over the full 256-wide row (each thread owns one row, so no cross-thread reduction).
+//     residual + LayerNorm over the full 256-wide row (each thread owns one row, so no cross-thread reduction), and
+//     write split16 (optionally with the value-projection blocks transposed for the attention kernels).
 // The kernel is templated on the A-operand addressing mode so that each instantiation carries exactly one loader
 // (an earlier all-modes-in-one kernel was ~30k SASS instructions and instruction-cache bound, profiles/r01_*).
 #include <cmath>
@@ -30,7 +32,7 @@
 
 namespace cotr {
 
-int g_tc_variant = 0;   // bring-up switch: bit0 swaps the LBO / SBO fields of the shared-memory descriptors
+int g_tc_variant = 0;                   // bring-up switch (unused bits reserved)
 long long* g_tc_timestamps = nullptr;   // debug: 64 clock64() stamps per CTA (cotr_debug_set_timestamps), else null
 
 namespace {
@@ -44,7 +46,7 @@ constexpr uint32_t kALbo = BM * 16 + 16;       // padded: 8 lanes writing the 8 
 constexpr uint32_t kAPlane = 8 * kALbo;        // one fp16 plane (hi or lo) of the 128 x 64 A tile
 constexpr uint32_t kSbo = 128;                 // 8 rows x 16 bytes
 
-enum LoaderMode : int { LD_GATHER = 0, LD_CONV = 1, LD_GENERIC = 2 };
+enum LoaderMode : int { LD_GATHER = 0, LD_CONV = 1, LD_STEM = 2 };
 
 __host__ __device__ inline int tc_npad(int N) { return N >= 64 ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16; }
 __host__ __device__ inline int tc_block_rows(int N) { return N >= 64 ? 64 : tc_npad(N); }
@@ -66,54 +68,8 @@ struct Cfg {
     static_assert(kAccCols <= 512, "TMEM has 512 columns");
 };
 
-// ---- A-operand fetch: 8 rows x 8 consecutive k (two float4) per thread and K chunk ------------------------------
-template <int MODE>
-__device__ __forceinline__ void fetch_a(const GemmParams& p, const ARow (&rows)[8], int k0, int kg, float4 (&buf)[16]) {
-    if constexpr (MODE == LD_GATHER) {
-        const int k = k0 + kg * 8;
-        const bool k_ok = k < p.K;                 // K % 8 == 0 on this path
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (rows[i].valid && k_ok) {
-                v0 = __ldg(reinterpret_cast<const float4*>(rows[i].base + k));
-                v1 = __ldg(reinterpret_cast<const float4*>(rows[i].base + k + 4));
-            }
-            buf[2 * i] = v0;
-            buf[2 * i + 1] = v1;
-        }
-    } else if constexpr (MODE == LD_CONV) {
-        // C % 64 == 0: a 64-wide K chunk lies inside one filter tap
-        const int tap = k0 / p.C;
-        const int c0 = k0 - tap * p.C + kg * 8;
-        const int kh = tap / p.KW;
-        const int kw = tap - kh * p.KW;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            const int ih = rows[i].ih0 + kh, iw = rows[i].iw0 + kw;
-            if (rows[i].valid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
-                const float* src = rows[i].base + ((size_t)ih * p.W + iw) * p.C + c0;
-                v0 = __ldg(reinterpret_cast<const float4*>(src));
-                v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-            }
-            buf[2 * i] = v0;
-            buf[2 * i + 1] = v1;
-        }
-    } else {
-#pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
-            buf[2 * i] = load_a4(p, rows[i], k0 + kg * 8);
-            buf[2 * i + 1] = load_a4(p, rows[i], k0 + kg * 8 + 4);
-        }
-    }
-}
-
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
 template <int BN, bool LN, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p, const int npad, const int variant,
-                                                              long long* __restrict__ ts) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p, const int npad, long long* __restrict__ ts) {
     using C = Cfg<BN>;
     // debug timeline (ts != null): slot layout documented in tools/bringup.py::gemm_timeline
     long long* my_ts = ts ? ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -150,110 +106,145 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     if (threadIdx.x == 0) COTR_TS(1);
 
     if (warp < 4) {
-        // ================= A producer: fp32 global -> fp16 hi/lo core-matrix rows in shared memory ============
+        // ================= A producer ===========================================================================
         const int t = threadIdx.x;
         const int kg = t & 7;          // 16-byte K group (8 halves) inside the 64-wide chunk
         const int rb = t >> 3;         // rows rb, rb+16, ..., rb+112
         ARow rows[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rows[i] = decode_a_row(p, m0 + rb + 16 * i);
-
-        float4 cur[16], nxt[16];
-        fetch_a<MODE>(p, rows, 0, kg, cur);
+        const uint32_t dst0 = smem_u32(stage_base) + (uint32_t)kg * kALbo + (uint32_t)rb * 16u;
         if (threadIdx.x == 0) COTR_TS(2);
+
 #pragma unroll 1
         for (int it = 0; it < KC; ++it) {
             const int s = it % C::kStages;
             const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-            if (it + 1 < KC) fetch_a<MODE>(p, rows, (it + 1) * BK, kg, nxt);
             mbar_wait(&empty[s], ph ^ 1u);
             if (threadIdx.x == 0 && it < 8) COTR_TS(3 + 2 * it);
-            uint8_t* a_hi = stage_base + (size_t)s * C::kStage + (uint32_t)kg * kALbo + (uint32_t)rb * 16u;
-            uint8_t* a_lo = a_hi + kAPlane;
+            const int k0 = it * BK;
+            if constexpr (MODE != LD_STEM) {
+                const uint32_t dst = dst0 + (uint32_t)s * C::kStage;
+                int kh = 0, kw = 0, koff = k0 + kg * 8;          // LD_GATHER: koff = column inside the row
+                if constexpr (MODE == LD_CONV) {                 // C % 64 == 0: the chunk lies inside one filter tap
+                    const int tap = k0 / p.C;
+                    koff = k0 - tap * p.C + kg * 8;
+                    kh = tap / p.KW;
+                    kw = tap - kh * p.KW;
+                }
+                const bool k_ok = (k0 + kg * 8) < p.K;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 v0 = cur[2 * i], v1 = cur[2 * i + 1];
-                uint4 hi, lo;
-                split_f16x2(v0.x, v0.y, hi.x, lo.x);
-                split_f16x2(v0.z, v0.w, hi.y, lo.y);
-                split_f16x2(v1.x, v1.y, hi.z, lo.z);
-                split_f16x2(v1.z, v1.w, hi.w, lo.w);
-                *reinterpret_cast<uint4*>(a_hi + i * 256) = hi;      // 16 rows x 16 bytes further down
-                *reinterpret_cast<uint4*>(a_lo + i * 256) = lo;
+                for (int i = 0; i < 8; ++i) {
+                    bool ok = rows[i].valid && k_ok;
+                    size_t off = rows[i].off + koff;
+                    if constexpr (MODE == LD_CONV) {
+                        const int ih = rows[i].ih0 + kh, iw = rows[i].iw0 + kw;
+                        ok = ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+                        off = rows[i].off + ((size_t)ih * p.W + iw) * p.C + koff;
+                    }
+                    if (!ok) off = 0;                            // src-size 0 -> 16 bytes of zeros, address unused
+                    const uint32_t bytes = ok ? 16u : 0u;
+                    cp_async16(dst + i * 256, p.a.hi + off, bytes);
+                    cp_async16(dst + kAPlane + i * 256, p.a.lo + off, bytes);
+                }
+                cp_async_mbar_arrive_noinc(&full_a[s]);
+            } else {
+                uint8_t* a_hi = stage_base + (size_t)s * C::kStage + (uint32_t)kg * kALbo + (uint32_t)rb * 16u;
+                uint8_t* a_lo = a_hi + kAPlane;
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v0 = load_stem4(p, rows[i], k0 + kg * 8);
+                    const float4 v1 = load_stem4(p, rows[i], k0 + kg * 8 + 4);
+                    uint4 hi, lo;
+                    split_f16x2(v0.x, v0.y, hi.x, lo.x);
+                    split_f16x2(v0.z, v0.w, hi.y, lo.y);
+                    split_f16x2(v1.x, v1.y, hi.z, lo.z);
+                    split_f16x2(v1.z, v1.w, hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(a_hi + i * 256) = hi;
+                    *reinterpret_cast<uint4*>(a_lo + i * 256) = lo;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&full_a[s]);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(&full_a[s]);
             if (threadIdx.x == 0 && it < 8) COTR_TS(4 + 2 * it);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }
 
         // ================= epilogue: TMEM -> registers -> global =============================================
-        mbar_wait(accum_full, 0);
-        tcgen05_fence_after();
-        if (threadIdx.x == 0) COTR_TS(20);
         const int row = m0 + warp * 32 + lane;
         const bool row_ok = row < p.M;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
         const float* add_row = (row_ok && p.addmat) ? p.addmat + (size_t)(row % p.add_period) * p.ld_add : nullptr;
-        const float* res_row = (row_ok && p.residual) ? p.residual + (size_t)row * p.ldr : nullptr;
-        float* out_row = p.out + (size_t)(row_ok ? row : 0) * p.ldc;
+        const bool has_res = row_ok && p.res.hi != nullptr;
+        const size_t res_off = (size_t)(row_ok ? row : 0) * p.ldr;
         const float acc_scale = p.acc_scale;
+        mbar_wait(accum_full, 0);
+        tcgen05_fence_after();
+        if (threadIdx.x == 0) COTR_TS(20);
 
-        // v[0..15] = sum over all accumulators of columns [c, c+16)
+        // v[0..15] = acc_scale * (sum over all accumulators of columns [c, c+16)); all TMEM loads of the chunk are
+        // issued back to back and waited for once.
         auto load_acc = [&](int c, float (&v)[16]) {
+            uint32_t r[C::kMainAcc + 1][16];
             __syncwarp();
-            tmem_ld16(trow + c, v);
 #pragma unroll
-            for (int a = 1; a <= C::kMainAcc; ++a) {
-                float w2[16];
-                tmem_ld16(trow + a * BN + c, w2);
+            for (int a = 0; a <= C::kMainAcc; ++a) tmem_ld16_issue(trow + a * BN + c, r[a]);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += w2[j];
+            for (int a = 0; a <= C::kMainAcc; ++a) tmem_ld16_fence(r[a]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(r[0][j]);
+#pragma unroll
+                for (int a = 1; a <= C::kMainAcc; ++a) x += __uint_as_float(r[a][j]);
+                v[j] = x * acc_scale;
             }
         };
-        // x += src[0..15] (vectorised; all row operands are 16-byte aligned on this path)
-        auto add16 = [&](const float* src, float (&v)[16]) {
+        // v += bias / add-matrix / residual for columns [nb, nb+16) (N % 16 == 0 whenever these are present)
+        auto add_operands = [&](int nb, float (&v)[16]) {
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 t4 = ldg4(src + j);
-                v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                    v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                }
+            }
+            if (add_row) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(add_row + nb + j));
+                    v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                }
+            }
+            if (has_res) {
+                float r8[8];
+                load8_split(p.res, res_off + nb, r8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += r8[j];
+                load8_split(p.res, res_off + nb + 8, r8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[8 + j] += r8[j];
             }
         };
 
         if constexpr (!LN) {
-            const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 15) == 0 && (p.ld_add & 3) == 0 && (p.ldr & 3) == 0;
+            const bool tail = p.out_f32 != nullptr && (p.N & 15) != 0;      // only the N = 2 prediction head
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
                 load_acc(c, v);
                 const int nb = n0 + c;
                 if (!row_ok || nb >= p.N) continue;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] *= acc_scale;
-                if (vec_ok) {
-                    if (p.bias) add16(p.bias + nb, v);
-                    if (add_row) add16(add_row + nb, v);
-                    if (res_row) add16(res_row + nb, v);
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(out_row + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (!tail) {
+                    add_operands(nb, v);
                 } else {
 #pragma unroll 1
-                    for (int j = 0; j < 16; ++j) {
-                        if (nb + j >= p.N) break;
-                        float x = v[j];
-                        if (p.bias) x += __ldg(p.bias + nb + j);
-                        if (add_row) x += __ldg(add_row + nb + j);
-                        if (res_row) x += __ldg(res_row + nb + j);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        out_row[nb + j] = x;
-                    }
+                    for (int j = 0; j < 16 && nb + j < p.N; ++j)
+                        if (p.bias) v[j] += __ldg(p.bias + nb + j);
                 }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                store16(p, row, nb, v);
             }
         } else {
             // fused residual + LayerNorm (eps 1e-5, biased variance) over the 256 columns this thread owns
@@ -262,11 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
                 load_acc(c, v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] *= acc_scale;
-                if (p.bias) add16(p.bias + c, v);
-                if (add_row) add16(add_row + c, v);
-                if (res_row) add16(res_row + c, v);
+                if (row_ok) add_operands(c, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) sum += v[j];
                 tmem_st16(trow + c, v);
@@ -294,14 +281,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 if (!row_ok) continue;
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float4 g4 = ldg4(p.ln_gamma + c + j), b4 = ldg4(p.ln_beta + c + j);
-                    float4 o;
-                    o.x = (v[j] - mean) * rstd * g4.x + b4.x;
-                    o.y = (v[j + 1] - mean) * rstd * g4.y + b4.y;
-                    o.z = (v[j + 2] - mean) * rstd * g4.z + b4.z;
-                    o.w = (v[j + 3] - mean) * rstd * g4.w + b4.w;
-                    *reinterpret_cast<float4*>(out_row + c + j) = o;
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c + j));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c + j));
+                    v[j] = (v[j] - mean) * rstd * g4.x + b4.x;
+                    v[j + 1] = (v[j + 1] - mean) * rstd * g4.y + b4.y;
+                    v[j + 2] = (v[j + 2] - mean) * rstd * g4.z + b4.z;
+                    v[j + 3] = (v[j + 3] - mean) * rstd * g4.w + b4.w;
                 }
+                store16(p, row, c, v);
             }
         }
         if (threadIdx.x == 0) COTR_TS(21);
@@ -333,6 +320,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             constexpr uint32_t idesc = make_idesc_f16_f32(BM, C::kNB);
             constexpr uint32_t b_lbo = C::kNB * 16;
             constexpr uint32_t b_plane = 8 * b_lbo;
+            const uint32_t hi_word = desc_hi(kSbo);
+            const uint32_t corr_col = tmem_base + (uint32_t)C::kMainAcc * BN;
 #pragma unroll 1
             for (int it = 0; it < KC; ++it) {
                 const int s = it % C::kStages;
@@ -341,26 +330,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 if (it < 8) COTR_TS(24 + 2 * it);
                 mbar_wait(&full_b[s], ph);
                 tcgen05_fence_after();
-                const uint32_t a_hi = smem_u32(stage_base + (size_t)s * C::kStage);
-                const uint32_t a_lo = a_hi + kAPlane;
-                const uint32_t b_base = a_hi + 2 * kAPlane;
+                const uint32_t a_addr = smem_u32(stage_base + (size_t)s * C::kStage);
+                // descriptor low words of the first K step; later K steps / planes / blocks only add to the address field
+                const uint32_t a_hi_lo = desc_lo(a_addr, kALbo);
+                const uint32_t b_hi_lo = desc_lo(a_addr + 2 * kAPlane, b_lbo);
 #pragma unroll
                 for (int ks = 0; ks < BK / 16; ++ks) {
                     const int g = it * (BK / 16) + ks;                       // global K step
-                    const uint32_t ao = ks * 2 * kALbo, bo = ks * 2 * b_lbo;
-                    const uint64_t dah = (variant & 1) ? make_smem_desc(a_hi + ao, kSbo, kALbo) : make_smem_desc(a_hi + ao, kALbo, kSbo);
-                    const uint64_t dal = (variant & 1) ? make_smem_desc(a_lo + ao, kSbo, kALbo) : make_smem_desc(a_lo + ao, kALbo, kSbo);
-                    const uint32_t main_col = (uint32_t)(g % C::kMainAcc) * BN;
-                    const uint32_t corr_col = (uint32_t)C::kMainAcc * BN;
+                    const uint32_t a_h = a_hi_lo + ((ks * 2 * kALbo) >> 4);
+                    const uint32_t a_l = a_h + (kAPlane >> 4);
+                    const uint64_t dah = make_desc(a_h, hi_word), dal = make_desc(a_l, hi_word);
+                    const uint32_t main_col = tmem_base + (uint32_t)(g % C::kMainAcc) * BN;
 #pragma unroll
                     for (int j = 0; j < C::kBlocks; ++j) {
-                        const uint32_t bh = b_base + j * C::kBBlock + bo, bl = bh + b_plane;
-                        const uint64_t dbh = (variant & 1) ? make_smem_desc(bh, kSbo, b_lbo) : make_smem_desc(bh, b_lbo, kSbo);
-                        const uint64_t dbl = (variant & 1) ? make_smem_desc(bl, kSbo, b_lbo) : make_smem_desc(bl, b_lbo, kSbo);
-                        const uint32_t col = tmem_base + j * C::kNB;
-                        umma_f16_ss(col + corr_col, dal, dbh, idesc, g != 0);
-                        umma_f16_ss(col + corr_col, dah, dbl, idesc, true);
-                        umma_f16_ss(col + main_col, dah, dbh, idesc, g >= C::kMainAcc);
+                        const uint32_t b_h = b_hi_lo + ((j * C::kBBlock + ks * 2 * b_lbo) >> 4);
+                        const uint64_t dbh = make_desc(b_h, hi_word), dbl = make_desc(b_h + (b_plane >> 4), hi_word);
+                        umma_f16_ss(corr_col + j * C::kNB, dal, dbh, idesc, g != 0);
+                        umma_f16_ss(corr_col + j * C::kNB, dah, dbl, idesc, true);
+                        umma_f16_ss(main_col + j * C::kNB, dah, dbh, idesc, g >= C::kMainAcc);
                     }
                 }
                 umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
@@ -389,7 +376,7 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     }
     const int npad = tc_npad(p.N);
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-    gemm_tc_kernel<BN, LN, MODE><<<grid, kThreads, C::kSmemBytes, s>>>(p, npad, g_tc_variant, g_tc_timestamps);
+    gemm_tc_kernel<BN, LN, MODE><<<grid, kThreads, C::kSmemBytes, s>>>(p, npad, g_tc_timestamps);
     COTR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -397,12 +384,14 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
 template <int BN, bool LN>
 int launch_mode(const GemmParams& p, cudaStream_t s) {
     const bool gather = (p.a_mode == A_ROWMAJOR || p.a_mode == A_TOKENS);
-    if (gather && (p.K & 7) == 0 && (p.lda & 3) == 0) return launch_one<BN, LN, LD_GATHER>(p, s);
+    if (gather && (p.K & 7) == 0 && (p.lda & 7) == 0) return launch_one<BN, LN, LD_GATHER>(p, s);
     if constexpr (!LN && BN >= 64) {
         if (p.a_mode == A_CONV_NHWC && (p.C & 63) == 0) return launch_one<BN, LN, LD_CONV>(p, s);
     }
-    if constexpr (!LN && BN == 64) return launch_one<64, false, LD_GENERIC>(p, s);
-    set_error("gemm_tc: no kernel instantiation for a_mode %d, K %d, lda %d with tile N %d", p.a_mode, p.K, p.lda, BN);
+    if constexpr (!LN && BN == 64) {
+        if (p.a_mode == A_STEM_NCHW) return launch_one<64, false, LD_STEM>(p, s);
+    }
+    set_error("gemm_tc: no kernel instantiation for a_mode %d, K %d, lda %d, C %d with tile N %d", p.a_mode, p.K, p.lda, p.C, BN);
     return 1;
 }
 
@@ -487,10 +476,12 @@ float tc_pack_weight(const float* w, int N, int K, void* dst_host) {
 int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     COTR_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "gemm_tc: empty problem %d x %d x %d", p.M, p.N, p.K);
     COTR_CHECK(p.Wtc != nullptr, "gemm_tc: weight has no tensor-core image");
-    COTR_CHECK(p.a_mode != A_CONV_NHWC || (p.C & 3) == 0, "gemm_tc: NHWC conv needs C %% 4 == 0 (C=%d)", p.C);
+    COTR_CHECK(p.out_f32 != nullptr || (p.N & 15) == 0, "gemm_tc: split16 outputs need N %% 16 == 0 (N=%d)", p.N);
+    COTR_CHECK(p.res.hi == nullptr || ((p.ldr & 7) == 0 && (p.N & 15) == 0), "gemm_tc: residual needs ldr %% 8 == 0");
+    COTR_CHECK(p.addmat == nullptr || ((p.ld_add & 3) == 0 && (p.N & 15) == 0), "gemm_tc: add-matrix needs ld %% 4 == 0");
+    COTR_CHECK(p.out_f32 != nullptr || (p.ldc & 7) == 0, "gemm_tc: split16 output needs ldc %% 8 == 0");
     if (p.ln_gamma) {
-        COTR_CHECK(p.N == 256 && p.ldc == 256 && p.relu == 0, "gemm_tc: LayerNorm epilogue needs N = ldc = 256");
-        COTR_CHECK((p.ldr & 3) == 0 && (p.ld_add & 3) == 0, "gemm_tc: LayerNorm epilogue needs 16-byte aligned row operands");
+        COTR_CHECK(p.N == 256 && p.relu == 0 && p.out_f32 == nullptr && !p.remap, "gemm_tc: LayerNorm epilogue needs N = 256");
         return launch_mode<256, true>(p, s);
     }
     if (p.N < 64) {

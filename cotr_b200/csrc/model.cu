@@ -26,8 +26,9 @@ void set_error(const char* fmt, ...) {
 namespace {
 
 constexpr int kDecodeChunkRows = 32768;   // decoder rows processed per pass (rows are independent, so chunking is exact)
-constexpr int kKvCols = kDecLayers * 2 * kDModel;    // 3072: [layer][K | V][256]
+constexpr int kKCols = kDecLayers * kDModel;         // 1536: K of all decoder layers, [layer][256]
 constexpr int kQpCols = kDecLayers * kDModel;        // 1536
+constexpr size_t kVtLayer = (size_t)kDModel * kTokens;   // one transposed value projection [256][512]
 
 struct DevConv {
     float* w = nullptr;    // [cout][kh][kw][cin], FrozenBN scale folded in
@@ -63,16 +64,20 @@ struct DecLayer {
     float *ln2_g, *ln2_b, *ln3_g, *ln3_b;
 };
 
+const Split16 kNoSplit = {nullptr, nullptr};
+
 struct Workspace {
     int cap_pairs = 0;
     int cap_rows = 0;
-    // backbone (per image sizes x 2*cap_pairs)
-    float *stem = nullptr, *bx = nullptr, *by = nullptr, *bt1 = nullptr, *bt2 = nullptr, *bds = nullptr;
+    // backbone (per image sizes x 2*cap_pairs), all split16
+    Split16 stem = kNoSplit, bx = kNoSplit, by = kNoSplit, bt1 = kNoSplit, bt2 = kNoSplit, bds = kNoSplit;
     // encoder
-    float *src = nullptr, *xa = nullptr, *xb = nullptr, *qkv = nullptr, *ao = nullptr, *ffh = nullptr, *tmp = nullptr;
+    Split16 src = kNoSplit, xa = kNoSplit, xb = kNoSplit, qk = kNoSplit, vt = kNoSplit, ao = kNoSplit, ffh = kNoSplit;
+    float* ln_tmp = nullptr;      // fp32 [tokens][256]: pre-LayerNorm rows of the SIMT cross-check path
     // decoder
-    float *qpos = nullptr, *qp = nullptr, *t = nullptr, *qb = nullptr, *dao = nullptr, *dtmp = nullptr, *dh = nullptr,
-          *hs = nullptr, *hd1 = nullptr, *hd2 = nullptr;
+    Split16 qpos = kNoSplit, qp = kNoSplit, t = kNoSplit, qb = kNoSplit, dao = kNoSplit, dh = kNoSplit, hs = kNoSplit,
+            hd1 = kNoSplit, hd2 = kNoSplit;
+    float* dln_tmp = nullptr;
     // host-buffer entry point staging
     float *img_stage = nullptr, *q_stage = nullptr, *pred_stage = nullptr;
     size_t img_stage_elems = 0, q_stage_elems = 0;
@@ -83,9 +88,10 @@ struct Workspace {
 
 struct cotr_context {
     cotr_model* model = nullptr;
-    float* kv = nullptr;        // [max_pairs * 512][3072]
+    cotr::Split16 k = cotr::kNoSplit;    // [max_pairs * 512][6 * 256]
+    cotr::Split16 vt = cotr::kNoSplit;   // [max_pairs][6][256][512]  (value projections stored transposed)
     int max_pairs = 0;
-    int pairs = 0;              // pairs encoded by the last cotr_encode_context
+    int pairs = 0;                       // pairs encoded by the last cotr_encode_context
 };
 
 struct cotr_model {
@@ -97,18 +103,18 @@ struct cotr_model {
     std::vector<cotr::Block> blocks;
     cotr::DevLinear proj;
     cotr::EncLayer enc[cotr::kEncLayers];
-    cotr::DevLinear kv_all;     // [3072][256], bias folded into add_kv
+    cotr::DevLinear kv_all;     // [3072][256] rows [l*512, l*512+256) = Wk_l, [l*512+256, l*512+512) = Wv_l
     float* add_kv = nullptr;    // [512][3072]
     cotr::DevLinear qpos_all;   // [1536][256] pre-scaled, bias pre-scaled
     cotr::DecLayer dec[cotr::kDecLayers];
     float *dec_norm_g = nullptr, *dec_norm_b = nullptr;
     cotr::DevLinear head[3];
-    float* pos = nullptr;       // [512][256] grid position embedding
+    float* pos = nullptr;       // [512][256] grid position embedding (fp32, debug / tests)
     cotr::Workspace ws;
     cotr_context* own_ctx = nullptr;
     cudaStream_t host_stream = nullptr;
-    const float* last_feat = nullptr;
-    const float* last_mem = nullptr;
+    cotr::Split16 last_feat = cotr::kNoSplit;
+    cotr::Split16 last_mem = cotr::kNoSplit;
     int last_pairs = 0, last_rows = 0;
     // per-launch profiler (cotr_profile_begin / cotr_profile_end): CUDA event pairs on the launching stream
     bool prof_on = false;
@@ -226,7 +232,7 @@ std::vector<float> grid_position_table() {
 }
 
 // ----------------------------------------------------------------------------------------------
-// launch helpers (all kernel launches of the forward go through these, so they can be counted)
+// launch helpers (all kernel launches of the forward go through these, so they can be counted / profiled)
 // ----------------------------------------------------------------------------------------------
 struct Run {
     cotr_model* m;
@@ -259,62 +265,60 @@ struct LaunchScope {
     }
 };
 
-GemmParams gemm_base(int M, int N, int K, const float* A, int lda, const float* W, const void* Wtc, float wtc_scale,
-                     float* out, int ldc) {
+GemmParams gemm_base(int M, int N, int K, CSplit16 A, int lda, const float* W, const void* Wtc, float wtc_scale,
+                     Split16 out, int ldc) {
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.acc_scale = wtc_scale;
     p.M = M; p.N = N; p.K = K;
-    p.A = A; p.a_mode = A_ROWMAJOR; p.lda = lda;
-    p.Wt = W; p.Wtc = Wtc;
+    p.a = A; p.a_mode = A_ROWMAJOR; p.lda = lda;
+    p.Wt = W; p.Wtc = Wtc; p.acc_scale = wtc_scale;
     p.out = out; p.ldc = ldc;
     p.add_period = 1;
     return p;
 }
 
+// ln_scratch: fp32 [M][256] staging for the SIMT path (the tensor-core GEMM fuses LayerNorm into its epilogue).
 int run_gemm(const Run& r, GemmParams p, float* ln_scratch) {
-    // The tensor-core GEMM fuses LayerNorm into its epilogue; the SIMT path runs it as a separate kernel.
     if (r.m->gemm_path == 0) {
         LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
         return launch_gemm_tc(p, r.s);
     }
     const float* g = p.ln_gamma;
     const float* b = p.ln_beta;
-    float* final_out = p.out;
     if (g) {
-        COTR_CHECK(p.N == kDModel && p.ldc == kDModel && ln_scratch != nullptr, "run_gemm: LayerNorm epilogue needs N = 256");
+        COTR_CHECK(p.N == kDModel && ln_scratch != nullptr, "run_gemm: LayerNorm epilogue needs N = 256");
         p.ln_gamma = nullptr; p.ln_beta = nullptr;
-        p.out = ln_scratch;
     }
     {
         LaunchScope scope(r, K_GEMM_SIMT, p.M, p.N, p.K);
-        if (launch_gemm_simt(p, r.s)) return 1;
+        if (launch_gemm_simt_raw(p, g ? ln_scratch : nullptr, r.s)) return 1;
     }
     if (g) {
         LaunchScope scope(r, K_LAYERNORM, p.M, kDModel, 0);
-        if (launch_layernorm(ln_scratch, nullptr, g, b, final_out, p.M, r.s)) return 1;
+        if (launch_layernorm_f32(ln_scratch, g, b, Split16{p.out.hi, p.out.lo}, p.M, r.s)) return 1;
     }
     return 0;
 }
 
-int run_linear(const Run& r, const DevLinear& L, int M, const float* A, int lda, float* out, int ldc, bool relu,
-               const float* residual = nullptr, int ldr = 0, const float* ln_g = nullptr, const float* ln_b = nullptr,
-               float* ln_scratch = nullptr) {
+int run_linear(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda, Split16 out, int ldc, bool relu,
+               CSplit16 residual = CSplit16{nullptr, nullptr}, int ldr = 0, const float* ln_g = nullptr,
+               const float* ln_b = nullptr, float* ln_scratch = nullptr) {
     GemmParams p = gemm_base(M, L.n, L.k, A, lda, L.w, L.wtc, L.wtc_scale, out, ldc);
     p.bias = L.b;
     p.relu = relu ? 1 : 0;
-    p.residual = residual; p.ldr = ldr;
+    p.res = residual; p.ldr = ldr;
     p.ln_gamma = ln_g; p.ln_beta = ln_b;
     return run_gemm(r, p, ln_scratch);
 }
 
-int run_conv(const Run& r, const DevConv& c, int n_img, const float* in, int H, int W, float* out, bool relu,
-             const float* residual, bool stem_nchw = false) {
+int run_conv(const Run& r, const DevConv& c, int n_img, CSplit16 in, const float* in_f32, int H, int W, Split16 out,
+             bool relu, CSplit16 residual) {
     const int OH = (H + 2 * c.pad - c.kh) / c.stride + 1;
     const int OW = (W + 2 * c.pad - c.kw) / c.stride + 1;
     GemmParams p = gemm_base(n_img * OH * OW, c.cout, c.kh * c.kw * c.cin, in, c.cin, c.w, c.wtc, c.wtc_scale, out, c.cout);
-    if (stem_nchw) {
+    if (in_f32) {
         p.a_mode = A_STEM_NCHW;
+        p.a_f32 = in_f32;
     } else if (c.kh == 1 && c.kw == 1 && c.stride == 1) {
         p.a_mode = A_ROWMAJOR;          // NHWC 1x1 convolution is a plain GEMM over pixels
     } else {
@@ -324,7 +328,7 @@ int run_conv(const Run& r, const DevConv& c, int n_img, const float* in, int H, 
     p.KH = c.kh; p.KW = c.kw; p.stride = c.stride; p.pad = c.pad;
     p.bias = c.b;
     p.relu = relu ? 1 : 0;
-    p.residual = residual; p.ldr = c.cout;
+    p.res = residual; p.ldr = c.cout;
     return run_gemm(r, p, nullptr);
 }
 
@@ -343,33 +347,44 @@ constexpr size_t kBigElems = 64 * 64 * 256;        // largest block input / outp
 constexpr size_t kT1Elems = 64 * 64 * 128;         // largest conv1 output per image (layer2.0)
 constexpr size_t kT2Elems = 64 * 64 * 64;          // largest conv2 output per image (layer1)
 
-size_t encode_ws_floats(int B) {
+size_t encode_ws_elems(int B) {
     const size_t img = 2 * (size_t)B;
     const size_t tok = (size_t)B * kTokens;
-    return img * (kStemElems + 3 * kBigElems + kT1Elems + kT2Elems) + tok * (kDModel * 5 + 3 * kDModel + kFF);
+    return img * (kStemElems + 3 * kBigElems + kT1Elems + kT2Elems) + tok * (kDModel * 4 + 2 * kDModel + kFF) +
+           (size_t)B * kVtLayer + tok * kDModel /* fp32 LN scratch */;
 }
-size_t decode_ws_floats(int rows) {
-    return (size_t)rows * (kDModel * 8 + kQpCols + kFF);
+size_t decode_ws_elems(int rows) {
+    return (size_t)rows * (kDModel * 7 + kQpCols + kFF) + (size_t)rows * kDModel /* fp32 LN scratch */;
 }
 
-int ws_alloc(float** p, size_t elems) {
+// split16 buffer of `elems` elements: one allocation, hi plane first (elems is always a multiple of 8)
+int ws_alloc(Split16* t, size_t elems) {
+    __half* base = nullptr;
+    COTR_CHECK_CUDA(cudaMalloc((void**)&base, elems * 2 * sizeof(__half)));
+    t->hi = base;
+    t->lo = base + elems;
+    return 0;
+}
+void ws_free(Split16* t) { if (t->hi) { cudaFree(t->hi); } t->hi = nullptr; t->lo = nullptr; }
+int ws_alloc_f32(float** p, size_t elems) {
     COTR_CHECK_CUDA(cudaMalloc((void**)p, elems * sizeof(float)));
     return 0;
 }
-void ws_free(float** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+void ws_free_f32(float** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
 
 int ensure_encode_ws(cotr_model* m, int B) {
     Workspace& w = m->ws;
     if (B <= w.cap_pairs) return 0;
     COTR_CHECK_CUDA(cudaDeviceSynchronize());
-    float** bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qkv, &w.ao, &w.ffh, &w.tmp};
-    for (float** b : bufs) ws_free(b);
+    Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh};
+    for (Split16* b : bufs) ws_free(b);
+    ws_free_f32(&w.ln_tmp);
     const size_t img = 2 * (size_t)B, tok = (size_t)B * kTokens;
     if (ws_alloc(&w.stem, img * kStemElems) || ws_alloc(&w.bx, img * kBigElems) || ws_alloc(&w.by, img * kBigElems) ||
         ws_alloc(&w.bds, img * kBigElems) || ws_alloc(&w.bt1, img * kT1Elems) || ws_alloc(&w.bt2, img * kT2Elems) ||
         ws_alloc(&w.src, tok * kDModel) || ws_alloc(&w.xa, tok * kDModel) || ws_alloc(&w.xb, tok * kDModel) ||
-        ws_alloc(&w.qkv, tok * 3 * kDModel) || ws_alloc(&w.ao, tok * kDModel) || ws_alloc(&w.ffh, tok * kFF) ||
-        ws_alloc(&w.tmp, tok * kDModel))
+        ws_alloc(&w.qk, tok * 2 * kDModel) || ws_alloc(&w.vt, (size_t)B * kVtLayer) || ws_alloc(&w.ao, tok * kDModel) ||
+        ws_alloc(&w.ffh, tok * kFF) || ws_alloc_f32(&w.ln_tmp, tok * kDModel))
         return 1;
     w.cap_pairs = B;
     return 0;
@@ -379,13 +394,14 @@ int ensure_decode_ws(cotr_model* m, int rows) {
     Workspace& w = m->ws;
     if (rows <= w.cap_rows) return 0;
     COTR_CHECK_CUDA(cudaDeviceSynchronize());
-    float** bufs[] = {&w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dtmp, &w.dh, &w.hs, &w.hd1, &w.hd2};
-    for (float** b : bufs) ws_free(b);
-    const size_t R = rows;
+    Split16* bufs[] = {&w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2};
+    for (Split16* b : bufs) ws_free(b);
+    ws_free_f32(&w.dln_tmp);
+    const size_t R = ((size_t)rows + 7) & ~(size_t)7;
     if (ws_alloc(&w.qpos, R * kDModel) || ws_alloc(&w.qp, R * kQpCols) || ws_alloc(&w.t, R * kDModel) ||
-        ws_alloc(&w.qb, R * kDModel) || ws_alloc(&w.dao, R * kDModel) || ws_alloc(&w.dtmp, R * kDModel) ||
-        ws_alloc(&w.dh, R * kFF) || ws_alloc(&w.hs, R * kDModel) || ws_alloc(&w.hd1, R * kDModel) ||
-        ws_alloc(&w.hd2, R * kDModel))
+        ws_alloc(&w.qb, R * kDModel) || ws_alloc(&w.dao, R * kDModel) || ws_alloc(&w.dh, R * kFF) ||
+        ws_alloc(&w.hs, R * kDModel) || ws_alloc(&w.hd1, R * kDModel) || ws_alloc(&w.hd2, R * kDModel) ||
+        ws_alloc_f32(&w.dln_tmp, R * kDModel))
         return 1;
     w.cap_rows = rows;
     return 0;
@@ -403,30 +419,31 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
     Workspace& w = m->ws;
     Run r{m, s};
     const int n_img = 2 * B;
+    const CSplit16 none{nullptr, nullptr};
 
     // backbone.py:81-82: the two 256x256 halves go through the ResNet body as independent images.
     // Stem: conv 7x7/2 (+FrozenBN folded) + ReLU, then MaxPool 3x3/2  (torchvision resnet.py _forward_impl).
-    if (run_conv(r, m->stem, n_img, img, 256, 256, w.stem, true, nullptr, /*stem_nchw=*/true)) return 1;
+    if (run_conv(r, m->stem, n_img, none, img, 256, 256, w.stem, true, none)) return 1;
     {
         LaunchScope scope(r, K_MAXPOOL, n_img * 64 * 64, 64, 0);
-        if (launch_maxpool_3x3s2_nhwc(w.stem, w.bx, n_img, 128, 128, 64, s)) return 1;
+        if (launch_maxpool_3x3s2_nhwc(cs(w.stem), w.bx, n_img, 128, 128, 64, s)) return 1;
     }
 
-    float* x = w.bx;
-    float* y = w.by;
+    Split16 x = w.bx;
+    Split16 y = w.by;
     int H = 64, W = 64;
     for (const Block& b : m->blocks) {
         // torchvision Bottleneck (v1.5): 1x1 -> 3x3(stride) -> 1x1, + identity | downsample, ReLU
-        if (run_conv(r, b.c1, n_img, x, H, W, w.bt1, true, nullptr)) return 1;
-        if (run_conv(r, b.c2, n_img, w.bt1, H, W, w.bt2, true, nullptr)) return 1;
+        if (run_conv(r, b.c1, n_img, cs(x), nullptr, H, W, w.bt1, true, none)) return 1;
+        if (run_conv(r, b.c2, n_img, cs(w.bt1), nullptr, H, W, w.bt2, true, none)) return 1;
         const int OH = H / b.c2.stride, OW = W / b.c2.stride;
-        const float* identity = x;
+        CSplit16 identity = cs(x);
         if (b.has_ds) {
-            if (run_conv(r, b.ds, n_img, x, H, W, w.bds, false, nullptr)) return 1;
-            identity = w.bds;
+            if (run_conv(r, b.ds, n_img, cs(x), nullptr, H, W, w.bds, false, none)) return 1;
+            identity = cs(w.bds);
         }
-        if (run_conv(r, b.c3, n_img, w.bt2, OH, OW, y, true, identity)) return 1;
-        float* t = x; x = y; y = t;
+        if (run_conv(r, b.c3, n_img, cs(w.bt2), nullptr, OH, OW, y, true, identity)) return 1;
+        Split16 t = x; x = y; y = t;
         H = OH; W = OW;
     }
     m->last_feat = x;   // (2B,16,16,1024) NHWC
@@ -435,43 +452,52 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
     // and the flatten to token-major (transformer.py:50): row = pair*512 + i*32 + j.
     const int T = B * kTokens;
     {
-        GemmParams p = gemm_base(T, kDModel, 1024, x, 1024, m->proj.w, m->proj.wtc, m->proj.wtc_scale, w.src, kDModel);
+        GemmParams p = gemm_base(T, kDModel, 1024, cs(x), 1024, m->proj.w, m->proj.wtc, m->proj.wtc_scale, w.src, kDModel);
         p.a_mode = A_TOKENS;
         p.bias = m->proj.b;
         if (run_gemm(r, p, nullptr)) return 1;
     }
 
     // transformer.py:143-159 x6 (post-LN).  q = k = x + pos is folded into the constant add_qkv matrix.
-    const float* xin = w.src;      // layer input; norm1 output goes to xa, norm2 output (next input) to xb
+    // q | k land row-major in qk [T][512]; v lands transposed in vt [pair][256][512] (what P V needs as its B operand).
+    Split16 xin = w.src;      // layer input; norm1 output goes to xa, norm2 output (next input) to xb
     for (int l = 0; l < kEncLayers; ++l) {
         const EncLayer& e = m->enc[l];
         {
-            GemmParams p = gemm_base(T, 3 * kDModel, kDModel, xin, kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, w.qkv, 3 * kDModel);
+            GemmParams p = gemm_base(T, 3 * kDModel, kDModel, cs(xin), kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, w.qk, 2 * kDModel);
             p.addmat = e.add_qkv; p.add_period = kTokens; p.ld_add = 3 * kDModel;
+            p.remap = 1;
+            p.blk_map[0] = 0; p.blk_map[1] = kDModel; p.blk_map[2] = -1;
+            p.vt = w.vt; p.n_vt = 1;
             if (run_gemm(r, p, nullptr)) return 1;
         }
         AttnParams a;
-        a.q = w.qkv; a.ldq = 3 * kDModel;
-        a.k = w.qkv + kDModel; a.ldk = 3 * kDModel;
-        a.v = w.qkv + 2 * kDModel; a.ldv = 3 * kDModel;
+        a.q = cs(w.qk); a.ldq = 2 * kDModel;
+        a.k = offset(cs(w.qk), kDModel); a.ldk = 2 * kDModel;
+        a.vt = cs(w.vt); a.vt_pair_stride = kVtLayer;
         a.out = w.ao; a.ldo = kDModel;
         a.nq = kTokens; a.npairs = B; a.pair0 = 0;
         if (run_attention(r, a)) return 1;
-        float* x1 = w.xa;
-        float* x2 = w.xb;
         // x1 = LN1(x + out_proj(attn))
-        if (run_linear(r, e.o, T, w.ao, kDModel, x1, kDModel, false, xin, kDModel, e.ln1_g, e.ln1_b, w.tmp)) return 1;
+        if (run_linear(r, e.o, T, cs(w.ao), kDModel, w.xa, kDModel, false, cs(xin), kDModel, e.ln1_g, e.ln1_b, w.ln_tmp)) return 1;
         // x2 = LN2(x1 + W2 relu(W1 x1 + b1) + b2)
-        if (run_linear(r, e.l1, T, x1, kDModel, w.ffh, kFF, true)) return 1;
-        if (run_linear(r, e.l2, T, w.ffh, kFF, x2, kDModel, false, x1, kDModel, e.ln2_g, e.ln2_b, w.tmp)) return 1;
-        xin = x2;
+        if (run_linear(r, e.l1, T, cs(w.xa), kDModel, w.ffh, kFF, true)) return 1;
+        if (run_linear(r, e.l2, T, cs(w.ffh), kFF, w.xb, kDModel, false, cs(w.xa), kDModel, e.ln2_g, e.ln2_b, w.ln_tmp)) return 1;
+        xin = w.xb;
     }
     m->last_mem = xin;
 
-    // transformer.py:192-195: K_l = (mem + pos) Wk_l^T + bk_l, V_l = mem Wv_l^T + bv_l for all 6 decoder layers at once.
+    // transformer.py:192-195: K_l = (mem + pos) Wk_l^T + bk_l, V_l = mem Wv_l^T + bv_l for all 6 decoder layers in ONE
+    // GEMM (N = 3072): K blocks go row-major into ctx->k [T][1536], V blocks transposed into ctx->vt [pair][6][256][512].
     {
-        GemmParams p = gemm_base(T, kKvCols, kDModel, xin, kDModel, m->kv_all.w, m->kv_all.wtc, m->kv_all.wtc_scale, ctx->kv, kKvCols);
-        p.addmat = m->add_kv; p.add_period = kTokens; p.ld_add = kKvCols;
+        GemmParams p = gemm_base(T, 2 * kKCols, kDModel, cs(xin), kDModel, m->kv_all.w, m->kv_all.wtc, m->kv_all.wtc_scale, ctx->k, kKCols);
+        p.addmat = m->add_kv; p.add_period = kTokens; p.ld_add = 2 * kKCols;
+        p.remap = 1;
+        for (int l = 0; l < kDecLayers; ++l) {
+            p.blk_map[2 * l] = l * kDModel;
+            p.blk_map[2 * l + 1] = -(l + 1);
+        }
+        p.vt = ctx->vt; p.n_vt = kDecLayers;
         if (run_gemm(r, p, nullptr)) return 1;
     }
     ctx->pairs = B;
@@ -484,6 +510,7 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
     Workspace& w = m->ws;
     Run r{m, s};
     const int R = npairs * nq;
+    const CSplit16 none{nullptr, nullptr};
     // cotr_model.py:34-35 query_proj (lin_sine, depth 64)
     {
         LaunchScope scope(r, K_QENC, R, kDModel, 0);
@@ -491,37 +518,42 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
     }
     // q-side of transformer.py:192: ((t + qpos) Wq^T + bq) s  =  t (s Wq)^T + [qpos (s Wq)^T + s bq]; the bracket for
     // all 6 layers is one GEMM.
-    if (run_linear(r, m->qpos_all, R, w.qpos, kDModel, w.qp, kQpCols, false)) return 1;
+    if (run_linear(r, m->qpos_all, R, cs(w.qpos), kDModel, w.qp, kQpCols, false)) return 1;
 
     for (int l = 0; l < kDecLayers; ++l) {
         const DecLayer& d = m->dec[l];
-        const float* q = w.qp;      // layer 0: tgt = 0 (transformer.py:54), so q is the qpos projection alone
+        CSplit16 q = cs(w.qp);      // layer 0: tgt = 0 (transformer.py:54), so q is the qpos projection alone
         int ldq = kQpCols;
         if (l > 0) {
-            if (run_linear(r, d.q, R, w.t, kDModel, w.qb, kDModel, false, w.qp + l * kDModel, kQpCols)) return 1;
-            q = w.qb; ldq = kDModel;
+            if (run_linear(r, d.q, R, cs(w.t), kDModel, w.qb, kDModel, false, offset(cs(w.qp), (size_t)l * kDModel), kQpCols)) return 1;
+            q = cs(w.qb); ldq = kDModel;
         }
         AttnParams a;
         a.q = q; a.ldq = ldq;
-        a.k = ctx->kv + (size_t)l * 2 * kDModel; a.ldk = kKvCols;
-        a.v = ctx->kv + (size_t)l * 2 * kDModel + kDModel; a.ldv = kKvCols;
+        a.k = offset(cs(ctx->k), (size_t)l * kDModel); a.ldk = kKCols;
+        a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
         a.out = w.dao; a.ldo = kDModel;
         a.nq = nq; a.npairs = npairs; a.pair0 = pair0;
         if (run_attention(r, a)) return 1;
         // transformer.py:196-197: t = norm2(t + out_proj(attn))
-        if (run_linear(r, d.o, R, w.dao, kDModel, w.t, kDModel, false, l > 0 ? w.t : nullptr, kDModel, d.ln2_g, d.ln2_b, w.dtmp)) return 1;
+        if (run_linear(r, d.o, R, cs(w.dao), kDModel, w.t, kDModel, false, l > 0 ? cs(w.t) : none, kDModel, d.ln2_g, d.ln2_b, w.dln_tmp)) return 1;
         // transformer.py:198-200: t = norm3(t + linear2(relu(linear1(t))))
-        if (run_linear(r, d.l1, R, w.t, kDModel, w.dh, kFF, true)) return 1;
-        if (run_linear(r, d.l2, R, w.dh, kFF, w.t, kDModel, false, w.t, kDModel, d.ln3_g, d.ln3_b, w.dtmp)) return 1;
+        if (run_linear(r, d.l1, R, cs(w.t), kDModel, w.dh, kFF, true)) return 1;
+        if (run_linear(r, d.l2, R, cs(w.dh), kFF, w.t, kDModel, false, cs(w.t), kDModel, d.ln3_g, d.ln3_b, w.dln_tmp)) return 1;
     }
     // transformer.py:110-111 decoder.norm on the last level; cotr_model.py:38-39 corr_embed on that level only.
     {
         LaunchScope scope(r, K_LAYERNORM, R, kDModel, 0);
-        if (launch_layernorm(w.t, nullptr, m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
+        if (launch_layernorm(cs(w.t), m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
     }
-    if (run_linear(r, m->head[0], R, w.hs, kDModel, w.hd1, kDModel, true)) return 1;
-    if (run_linear(r, m->head[1], R, w.hd1, kDModel, w.hd2, kDModel, true)) return 1;
-    if (run_linear(r, m->head[2], R, w.hd2, kDModel, pred, 2, false)) return 1;
+    if (run_linear(r, m->head[0], R, cs(w.hs), kDModel, w.hd1, kDModel, true)) return 1;
+    if (run_linear(r, m->head[1], R, cs(w.hd1), kDModel, w.hd2, kDModel, true)) return 1;
+    {
+        GemmParams p = gemm_base(R, 2, kDModel, cs(w.hd2), kDModel, m->head[2].w, m->head[2].wtc, m->head[2].wtc_scale, kNoSplit, 2);
+        p.bias = m->head[2].b;
+        p.out_f32 = pred;
+        if (run_gemm(r, p, nullptr)) return 1;
+    }
     return 0;
 }
 
@@ -595,7 +627,7 @@ int build_model(cotr_model* m, const TensorMap& tm) {
         return make_linear(m, to_vec(w, (size_t)N * K), &bv, N, K, out);
     };
 
-    // temporary device buffers for the constant position-bias matrices, produced with the fp32 SIMT GEMM
+    // constant position-bias matrices, produced with the fp32 SIMT GEMM once per model
     struct PosBiasJob { std::vector<float> w_masked; std::vector<float> bias; int N; float** dst; };
     std::vector<PosBiasJob> jobs;
 
@@ -620,7 +652,8 @@ int build_model(cotr_model* m, const TensorMap& tm) {
             return 1;
     }
 
-    std::vector<float> kv_w((size_t)kKvCols * kDModel), kv_wm((size_t)kKvCols * kDModel, 0.f), kv_b(kKvCols);
+    const int kKvN = 2 * kKCols;   // 3072
+    std::vector<float> kv_w((size_t)kKvN * kDModel), kv_wm((size_t)kKvN * kDModel, 0.f), kv_b(kKvN);
     std::vector<float> qp_w((size_t)kQpCols * kDModel), qp_b(kQpCols);
     for (int l = 0; l < kDecLayers; ++l) {
         const std::string p = "transformer.decoder.layers." + std::to_string(l);
@@ -645,8 +678,8 @@ int build_model(cotr_model* m, const TensorMap& tm) {
             return 1;
         // decoder.layers.N.norm1.* exists in the checkpoint but transformer.py:185-201 never uses it.
     }
-    if (make_linear(m, kv_w, nullptr, kKvCols, kDModel, &m->kv_all)) return 1;
-    jobs.push_back({kv_wm, kv_b, kKvCols, &m->add_kv});
+    if (make_linear(m, kv_w, nullptr, kKvN, kDModel, &m->kv_all)) return 1;
+    jobs.push_back({kv_wm, kv_b, kKvN, &m->add_kv});
     if (make_linear(m, qp_w, &qp_b, kQpCols, kDModel, &m->qpos_all)) return 1;
     if (upload_vec(m, tm, "transformer.decoder.norm.weight", kDModel, &m->dec_norm_g) ||
         upload_vec(m, tm, "transformer.decoder.norm.bias", kDModel, &m->dec_norm_b))
@@ -655,7 +688,10 @@ int build_model(cotr_model* m, const TensorMap& tm) {
     if (linear_from("corr_embed.layers.1", kDModel, kDModel, &m->head[1])) return 1;
     if (linear_from("corr_embed.layers.2", 2, kDModel, &m->head[2])) return 1;
 
-    // add matrices: pos [512,256] x Wmasked^T + bias  (fp32 SIMT GEMM, once per model)
+    // add matrices: pos [512,256] x Wmasked^T + bias  (fp32 SIMT GEMM on the split16 pos table, fp32 result)
+    Split16 pos16 = kNoSplit;
+    if (ws_alloc(&pos16, (size_t)kTokens * kDModel)) return 1;
+    if (launch_f32_to_split16(m->pos, pos16, (size_t)kTokens * kDModel, 0)) return 1;
     for (PosBiasJob& j : jobs) {
         float *wd = nullptr, *bd = nullptr;
         COTR_CHECK_CUDA(cudaMalloc((void**)&wd, j.w_masked.size() * sizeof(float)));
@@ -663,13 +699,14 @@ int build_model(cotr_model* m, const TensorMap& tm) {
         COTR_CHECK_CUDA(cudaMemcpy(wd, j.w_masked.data(), j.w_masked.size() * sizeof(float), cudaMemcpyHostToDevice));
         COTR_CHECK_CUDA(cudaMemcpy(bd, j.bias.data(), j.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
         if (dev_alloc(m, (void**)j.dst, (size_t)kTokens * j.N * sizeof(float))) return 1;
-        GemmParams p = gemm_base(kTokens, j.N, kDModel, m->pos, kDModel, wd, nullptr, 1.f, *j.dst, j.N);
+        GemmParams p = gemm_base(kTokens, j.N, kDModel, cs(pos16), kDModel, wd, nullptr, 1.f, kNoSplit, j.N);
         p.bias = bd;
-        if (launch_gemm_simt(p, 0)) return 1;
+        if (launch_gemm_simt_raw(p, *j.dst, 0)) return 1;
         COTR_CHECK_CUDA(cudaDeviceSynchronize());
         cudaFree(wd);
         cudaFree(bd);
     }
+    ws_free(&pos16);
     return 0;
 }
 
@@ -684,7 +721,7 @@ using namespace cotr;
 extern "C" {
 
 const char* cotr_last_error(void) { return g_error; }
-const char* cotr_version(void) { return "cotr_b200 0.1 (sm_100a)"; }
+const char* cotr_version(void) { return "cotr_b200 0.2 (sm_100a)"; }
 
 int cotr_create(int device, const cotr_tensor* tensors, int n_tensors, cotr_model** out) {
     COTR_CHECK(out != nullptr && tensors != nullptr && n_tensors > 0, "cotr_create: bad arguments");
@@ -703,6 +740,7 @@ int cotr_create(int device, const cotr_tensor* tensors, int n_tensors, cotr_mode
     }
     cotr_model* m = new cotr_model();
     m->device = device;
+    g_error[0] = 0;
     if (build_model(m, tm) || cotr_context_create(m, 1, &m->own_ctx) ||
         cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
         if (g_error[0] == 0) set_error("cotr_create: stream creation failed");
@@ -720,10 +758,11 @@ void cotr_destroy(cotr_model* m) {
     if (m->own_ctx) cotr_context_destroy(m->own_ctx);
     for (void* p : m->allocs) cudaFree(p);
     Workspace& w = m->ws;
-    float** bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qkv, &w.ao, &w.ffh, &w.tmp,
-                      &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dtmp, &w.dh, &w.hs, &w.hd1, &w.hd2,
-                      &w.img_stage, &w.q_stage, &w.pred_stage};
-    for (float** b : bufs) ws_free(b);
+    Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh,
+                       &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2};
+    for (Split16* b : bufs) ws_free(b);
+    float** fbufs[] = {&w.ln_tmp, &w.dln_tmp, &w.img_stage, &w.q_stage, &w.pred_stage};
+    for (float** b : fbufs) ws_free_f32(b);
     if (m->host_stream) cudaStreamDestroy(m->host_stream);
     for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
     delete m;
@@ -735,9 +774,9 @@ int cotr_context_create(cotr_model* m, int max_pairs, cotr_context** out) {
     cotr_context* c = new cotr_context();
     c->model = m;
     c->max_pairs = max_pairs;
-    if (cudaMalloc((void**)&c->kv, (size_t)max_pairs * kTokens * kKvCols * sizeof(float)) != cudaSuccess) {
+    if (ws_alloc(&c->k, (size_t)max_pairs * kTokens * kKCols) || ws_alloc(&c->vt, (size_t)max_pairs * kDecLayers * kVtLayer)) {
         set_error("cotr_context_create: out of device memory for %d pairs", max_pairs);
-        delete c;
+        cotr_context_destroy(c);
         return 1;
     }
     *out = c;
@@ -746,7 +785,8 @@ int cotr_context_create(cotr_model* m, int max_pairs, cotr_context** out) {
 
 void cotr_context_destroy(cotr_context* c) {
     if (!c) return;
-    if (c->kv) cudaFree(c->kv);
+    ws_free(&c->k);
+    ws_free(&c->vt);
     delete c;
 }
 
@@ -785,14 +825,14 @@ int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries
     const size_t q_elems = (size_t)B * Q * 2;
     if (img_elems > w.img_stage_elems) {
         COTR_CHECK_CUDA(cudaDeviceSynchronize());
-        ws_free(&w.img_stage);
-        if (ws_alloc(&w.img_stage, img_elems)) return 1;
+        ws_free_f32(&w.img_stage);
+        if (ws_alloc_f32(&w.img_stage, img_elems)) return 1;
         w.img_stage_elems = img_elems;
     }
     if (q_elems > w.q_stage_elems) {
         COTR_CHECK_CUDA(cudaDeviceSynchronize());
-        ws_free(&w.q_stage); ws_free(&w.pred_stage);
-        if (ws_alloc(&w.q_stage, q_elems) || ws_alloc(&w.pred_stage, q_elems)) return 1;
+        ws_free_f32(&w.q_stage); ws_free_f32(&w.pred_stage);
+        if (ws_alloc_f32(&w.q_stage, q_elems) || ws_alloc_f32(&w.pred_stage, q_elems)) return 1;
         w.q_stage_elems = q_elems;
     }
     cudaStream_t s = m->host_stream;
@@ -808,7 +848,7 @@ size_t cotr_workspace_bytes(int B, int Q) {
     if (B < 1 || Q < 0) return 0;
     const long long total = (long long)B * Q;
     const int rows = (int)(total < kDecodeChunkRows ? total : kDecodeChunkRows);
-    return (encode_ws_floats(B) + decode_ws_floats(rows)) * sizeof(float);
+    return (encode_ws_elems(B) + decode_ws_elems(rows)) * sizeof(float);
 }
 
 int cotr_last_launch_count(const cotr_model* m) { return m ? m->launches : -1; }
@@ -835,24 +875,32 @@ int cotr_profile_end(cotr_model* m, cotr_launch_record* out, int max_records) {
         m->prof_records[i].ms = ms;
         out[i] = m->prof_records[i];
     }
-    return n >= 0 ? -n - 1 : 1;     // see header: success is encoded as -(count + 1)
+    return -n - 1;     // see header: success is encoded as -(count + 1)
 }
 
 int64_t cotr_debug_read(cotr_model* m, const char* name, float* out_host, int64_t max_elems) {
     if (!m || !name || !out_host) return -1;
     cudaSetDevice(m->device);
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    const float* src = nullptr;
+    CSplit16 src{nullptr, nullptr};
+    const float* src_f32 = nullptr;
     int64_t n = 0;
     const std::string s(name);
-    if (s == "feat") { src = m->last_feat; n = (int64_t)m->last_pairs * 2 * 16 * 16 * 1024; }
-    else if (s == "src") { src = m->ws.src; n = (int64_t)m->last_pairs * kTokens * kDModel; }
-    else if (s == "mem") { src = m->last_mem; n = (int64_t)m->last_pairs * kTokens * kDModel; }
-    else if (s == "hs") { src = m->ws.hs; n = (int64_t)m->last_rows * kDModel; }
-    else if (s == "pos") { src = m->pos; n = (int64_t)kTokens * kDModel; }
-    if (!src || n <= 0 || n > max_elems) return -1;
-    if (cudaMemcpy(out_host, src, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return n;
+    if (s == "feat") { src = cs(m->last_feat); n = (int64_t)m->last_pairs * 2 * 16 * 16 * 1024; }
+    else if (s == "src") { src = cs(m->ws.src); n = (int64_t)m->last_pairs * kTokens * kDModel; }
+    else if (s == "mem") { src = cs(m->last_mem); n = (int64_t)m->last_pairs * kTokens * kDModel; }
+    else if (s == "hs") { src = cs(m->ws.hs); n = (int64_t)m->last_rows * kDModel; }
+    else if (s == "pos") { src_f32 = m->pos; n = (int64_t)kTokens * kDModel; }
+    if ((!src.hi && !src_f32) || n <= 0 || n > max_elems) return -1;
+    float* tmp = nullptr;
+    if (!src_f32) {
+        if (cudaMalloc((void**)&tmp, n * sizeof(float)) != cudaSuccess) return -1;
+        if (launch_split16_to_f32(src, tmp, (size_t)n, 0) || cudaDeviceSynchronize() != cudaSuccess) { cudaFree(tmp); return -1; }
+        src_f32 = tmp;
+    }
+    const cudaError_t e = cudaMemcpy(out_host, src_f32, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (tmp) cudaFree(tmp);
+    return e == cudaSuccess ? n : -1;
 }
 
 int cotr_set_gemm_path(cotr_model* m, int path) {
@@ -864,22 +912,53 @@ int cotr_set_gemm_path(cotr_model* m, int path) {
 void cotr_debug_set_variant(int variant) { g_tc_variant = variant; }
 void cotr_debug_set_timestamps(void* dev_buffer) { g_tc_timestamps = reinterpret_cast<long long*>(dev_buffer); }
 
+// ---- kernel-level test hooks: fp32 device tensors in / out, converted to split16 around the kernel under test -------
+namespace {
+struct TmpSplit {
+    Split16 t = kNoSplit;
+    ~TmpSplit() { ws_free(&t); }
+    int from_f32(const float* src, size_t n) {
+        const size_t padded = (n + 7) & ~(size_t)7;
+        if (ws_alloc(&t, padded)) return 1;
+        return launch_f32_to_split16(src, t, n, 0);
+    }
+    int empty(size_t n) { return ws_alloc(&t, (n + 7) & ~(size_t)7); }
+};
+}  // namespace
+
 int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float* w_host, const float* bias_dev,
                    const float* addmat_dev, const float* residual_dev, const float* ln_gamma_dev,
                    const float* ln_beta_dev, float* out_dev) {
     COTR_CHECK(d && A_dev && w_host && out_dev, "cotr_test_gemm: null argument");
+    COTR_CHECK(d->ldc == d->N, "cotr_test_gemm: ldc must equal N");
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = d->M; p.N = d->N; p.K = d->K;
-    p.A = A_dev; p.a_mode = d->a_mode; p.lda = d->lda;
+    p.a_mode = d->a_mode; p.lda = d->lda;
     p.H = d->H; p.W = d->W; p.C = d->C; p.OH = d->OH; p.OW = d->OW;
     p.KH = d->KH; p.KW = d->KW; p.stride = d->stride; p.pad = d->pad;
     p.bias = bias_dev; p.addmat = addmat_dev; p.add_period = d->add_period > 0 ? d->add_period : 1; p.ld_add = d->ld_add;
-    p.residual = residual_dev; p.ldr = d->ldr; p.relu = d->relu;
+    p.ldr = d->ldr; p.relu = d->relu;
     p.ln_gamma = ln_gamma_dev; p.ln_beta = ln_beta_dev;
-    p.out = out_dev; p.ldc = d->ldc;
+    p.ldc = d->ldc;
+    TmpSplit a16, res16, out16;
+    if (d->a_mode == A_STEM_NCHW) {
+        p.a_f32 = A_dev;
+    } else {
+        COTR_CHECK(d->a_elems > 0, "cotr_test_gemm: a_elems missing");
+        if (a16.from_f32(A_dev, (size_t)d->a_elems)) return 1;
+        p.a = cs(a16.t);
+    }
+    if (residual_dev) {
+        if (res16.from_f32(residual_dev, (size_t)d->M * d->ldr)) return 1;
+        p.res = cs(res16.t);
+    }
+    const bool f32_out = (d->N & 15) != 0;
+    if (f32_out) p.out_f32 = out_dev;
+    else { if (out16.empty((size_t)d->M * d->N)) return 1; p.out = out16.t; }
     float* wd = nullptr;
     void* wtc = nullptr;
+    float* scratch = nullptr;
     const size_t wn = (size_t)d->N * d->K;
     COTR_CHECK_CUDA(cudaMalloc((void**)&wd, wn * sizeof(float)));
     COTR_CHECK_CUDA(cudaMemcpy(wd, w_host, wn * sizeof(float), cudaMemcpyHostToDevice));
@@ -895,24 +974,56 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
     } else {
         const float* g = p.ln_gamma; const float* b = p.ln_beta;
         p.ln_gamma = nullptr; p.ln_beta = nullptr;
-        rc = launch_gemm_simt(p, 0);
-        if (!rc && g) rc = launch_layernorm(p.out, nullptr, g, b, p.out, p.M, 0);
+        if (g) {
+            rc = cudaMalloc((void**)&scratch, (size_t)d->M * d->N * sizeof(float)) != cudaSuccess;
+            if (!rc) rc = launch_gemm_simt_raw(p, scratch, 0);
+            if (!rc) rc = launch_layernorm_f32(scratch, g, b, p.out, p.M, 0);
+        } else {
+            rc = launch_gemm_simt(p, 0);
+        }
     }
+    if (!rc && !f32_out) rc = launch_split16_to_f32(cs(out16.t), out_dev, (size_t)d->M * d->N, 0);
     cudaError_t e = cudaDeviceSynchronize();
     cudaFree(wd);
     cudaFree(wtc);
+    if (scratch) cudaFree(scratch);
     if (rc) return rc;
     COTR_CHECK(e == cudaSuccess, "cotr_test_gemm: kernel failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
+// q (npairs*nq,256), k / v (npairs*512,256) fp32 row-major; v is transposed into the [pair][256][512] layout first.
 int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const float* v_dev, float* out_dev,
                         int nq, int npairs) {
     COTR_CHECK(q_dev && k_dev && v_dev && out_dev, "cotr_test_attention: null argument");
+    TmpSplit q16, k16, vt16, o16;
+    const size_t qn = (size_t)npairs * nq * kDModel, kn = (size_t)npairs * kTokens * kDModel;
+    if (q16.from_f32(q_dev, qn) || k16.from_f32(k_dev, kn) || vt16.empty(kn) || o16.empty(qn)) return 1;
+    {   // transpose V with an identity "GEMM": vt = (V * I^T) stored through the transposed-block epilogue
+        std::vector<float> eye((size_t)kDModel * kDModel, 0.f);
+        for (int i = 0; i < kDModel; ++i) eye[(size_t)i * kDModel + i] = 1.f;
+        float* ed = nullptr;
+        COTR_CHECK_CUDA(cudaMalloc((void**)&ed, eye.size() * sizeof(float)));
+        COTR_CHECK_CUDA(cudaMemcpy(ed, eye.data(), eye.size() * sizeof(float), cudaMemcpyHostToDevice));
+        TmpSplit v16;
+        if (v16.from_f32(v_dev, kn)) { cudaFree(ed); return 1; }
+        GemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.M = npairs * kTokens; p.N = kDModel; p.K = kDModel;
+        p.a = cs(v16.t); p.a_mode = A_ROWMAJOR; p.lda = kDModel;
+        p.Wt = ed; p.acc_scale = 1.f; p.add_period = 1;
+        p.remap = 1; p.blk_map[0] = -1; p.vt = vt16.t; p.n_vt = 1; p.ldc = kDModel;
+        const int rc = launch_gemm_simt(p, 0);
+        cudaDeviceSynchronize();
+        cudaFree(ed);
+        if (rc) return rc;
+    }
     AttnParams a;
-    a.q = q_dev; a.ldq = kDModel; a.k = k_dev; a.ldk = kDModel; a.v = v_dev; a.ldv = kDModel;
-    a.out = out_dev; a.ldo = kDModel; a.nq = nq; a.npairs = npairs; a.pair0 = 0;
-    const int rc = path == 0 ? launch_attention_tc(a, 0) : launch_attention_simt(a, 0);
+    a.q = cs(q16.t); a.ldq = kDModel; a.k = cs(k16.t); a.ldk = kDModel;
+    a.vt = cs(vt16.t); a.vt_pair_stride = kVtLayer;
+    a.out = o16.t; a.ldo = kDModel; a.nq = nq; a.npairs = npairs; a.pair0 = 0;
+    int rc = path == 0 ? launch_attention_tc(a, 0) : launch_attention_simt(a, 0);
+    if (!rc) rc = launch_split16_to_f32(cs(o16.t), out_dev, qn, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (rc) return rc;
     COTR_CHECK(e == cudaSuccess, "cotr_test_attention: kernel failed: %s", cudaGetErrorString(e));

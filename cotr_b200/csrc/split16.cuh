@@ -1,0 +1,88 @@
+// fp32 <-> split16 (fp16 hi + fp16 lo) conversions and the GEMM epilogue store shared by the SIMT and tcgen05 kernels.
+#pragma once
+#include "common.cuh"
+
+namespace cotr {
+
+// x ~= hi + lo with ~22 mantissa bits.  |x| is clamped to the fp16 range for hi (lo then carries up to another
+// 65504); below 2^-3 the lo term is an fp16 subnormal, i.e. the absolute error floors at ~3e-8.
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split_f16(float a, __half& hi, __half& lo) {
+    hi = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f));
+    lo = __float2half_rn(a - __half2float(hi));
+}
+__device__ __forceinline__ float2 join_f16x2(uint32_t hi, uint32_t lo) {
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+    return make_float2(h.x + l.x, h.y + l.y);
+}
+__device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
+
+// 8 consecutive elements (16 bytes per plane) -> 8 floats
+__device__ __forceinline__ void load8_split(const CSplit16& t, size_t off, float (&v)[8]) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(t.hi + off));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(t.lo + off));
+    float2 f;
+    f = join_f16x2(h.x, l.x); v[0] = f.x; v[1] = f.y;
+    f = join_f16x2(h.y, l.y); v[2] = f.x; v[3] = f.y;
+    f = join_f16x2(h.z, l.z); v[4] = f.x; v[5] = f.y;
+    f = join_f16x2(h.w, l.w); v[6] = f.x; v[7] = f.y;
+}
+__device__ __forceinline__ void store8_split(const Split16& t, size_t off, const float* v) {
+    uint4 h, l;
+    split_f16x2(v[0], v[1], h.x, l.x);
+    split_f16x2(v[2], v[3], h.y, l.y);
+    split_f16x2(v[4], v[5], h.z, l.z);
+    split_f16x2(v[6], v[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(t.hi + off) = h;
+    *reinterpret_cast<uint4*>(t.lo + off) = l;
+}
+
+// Where column block [nb, nb+16) of output row `row` goes (GemmParams::remap / blk_map): returns true when the
+// block is a transposed value projection, in which case `base` is the vt element offset of (column nb, this row)
+// and consecutive columns are 512 elements apart; otherwise `base` is the row-major element offset.
+__device__ __forceinline__ bool out_location(const GemmParams& p, int row, int nb, size_t& base) {
+    int col = nb;
+    if (p.remap) {
+        const int m = p.blk_map[nb >> 8];
+        if (m < 0) {
+            const int pair = row >> 9, key = row & (kTokens - 1);
+            base = ((size_t)(pair * p.n_vt + (-m - 1)) * kDModel + (nb & 255)) * kTokens + key;
+            return true;
+        }
+        col = m + (nb & 255);
+    }
+    base = (size_t)row * p.ldc + col;
+    return false;
+}
+
+// Store 16 final values of columns [nb, nb+16) of `row` (split16 outputs need N % 16 == 0; the fp32 output is scalar).
+__device__ __forceinline__ void store16(const GemmParams& p, int row, int nb, const float (&v)[16]) {
+    if (p.out_f32) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (nb + j < p.N) p.out_f32[(size_t)row * p.ldc + nb + j] = v[j];
+        return;
+    }
+    size_t base;
+    if (out_location(p, row, nb, base)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {       // lanes hold consecutive keys -> each store is a coalesced 64-byte run
+            __half h, l;
+            split_f16(v[j], h, l);
+            p.vt.hi[base + (size_t)j * kTokens] = h;
+            p.vt.lo[base + (size_t)j * kTokens] = l;
+        }
+    } else {
+        store8_split(p.out, base, v);
+        store8_split(p.out, base + 8, v + 8);
+    }
+}
+
+}  // namespace cotr

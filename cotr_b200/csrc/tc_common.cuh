@@ -1,4 +1,4 @@
-// Thin inline-PTX layer for sm_100a: mbarrier, bulk TMA (cp.async.bulk), tcgen05 MMA / TMEM.
+// Thin inline-PTX layer for sm_100a: mbarrier, cp.async, bulk TMA (cp.async.bulk), tcgen05 MMA / TMEM.
 // No CUTLASS dependency; descriptor bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor".
 #pragma once
 #include <cuda_fp16.h>
@@ -46,6 +46,15 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- cp.async (LDGSTS): 16 bytes global -> shared, zero-filled when src_bytes == 0 --------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+// The mbarrier receives one arrival from this thread once all its cp.async issued so far have landed.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- bulk TMA: contiguous global -> shared, completion on an mbarrier --------------------------
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -68,13 +77,14 @@ __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fe
 // Shared-memory matrix descriptor, K-major, no swizzle.  Canonical layout in 16-byte units
 // ((8, n), 2) : ((1, SBO), LBO): a core matrix is 8 rows x 16 bytes stored contiguously (128 B),
 // SBO = byte distance between 8-row groups, LBO = byte distance between the two 16-byte K halves of one MMA.
+// Low word: start address >> 4 (bits 0-13), LBO >> 4 (bits 16-29).  High word: SBO >> 4 (bits 0-13), version 1 (bit 14).
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;    // descriptor version 1 (Blackwell)
-    return d;                  // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+    return make_desc(desc_lo(smem_addr, lbo_bytes), desc_hi(sbo_bytes));
 }
 
 // Instruction descriptor for kind::f16: FP16 x FP16 -> FP32 (a_format = b_format = 0), both operands K-major, dense.
@@ -100,15 +110,31 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ---- TMEM <-> registers: 32 lanes x 16 consecutive fp32 columns per warp --------------------------
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
+// tmem_ld16_issue starts the load; the registers may only be consumed after tmem_ld16_fence on the SAME array (the
+// fence is a tcgen05.wait::ld that carries the registers as in/out operands, so the compiler cannot move uses above it).
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_fence(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -122,17 +148,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// ---- fp32 -> (fp16 hi, fp16 lo) split: x ~= hi + lo with ~22 mantissa bits ------------------------------
-// |x| is clamped to the fp16 range for hi (lo then carries up to another 65504); below 2^-3 the lo term is an
-// fp16 subnormal, i.e. the absolute error floors at ~3e-8.
-__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 
 }  // namespace tc
 }  // namespace cotr

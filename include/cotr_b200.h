@@ -117,16 +117,18 @@ typedef struct cotr_test_gemm_desc {
     int32_t H, W, C, OH, OW, KH, KW, stride, pad;   /* convolution geometry for a_mode 1 / 2                  */
     int32_t relu;
     int32_t add_period, ld_add, ldr, ldc;
+    int64_t a_elems;              /* element count of the A activation tensor (a_mode 0 / 1 / 3)                 */
 } cotr_test_gemm_desc;
-/* out = epilogue(A * W^T): A/bias/addmat/residual/ln_* /out are DEVICE pointers (may be NULL where optional),
- * w_host is a HOST [N,K] matrix (packed for the tensor-core path internally). */
+/* out = epilogue(A * W^T): A/bias/addmat/residual/ln_* /out are fp32 DEVICE pointers (may be NULL where optional) -
+ * the hook converts activations to / from the library's split16 storage around the kernel under test; w_host is a HOST
+ * [N,K] matrix (packed for the tensor-core path internally). */
 int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float* w_host, const float* bias_dev,
                    const float* addmat_dev, const float* residual_dev, const float* ln_gamma_dev,
                    const float* ln_beta_dev, float* out_dev);
 /* out[(p*nq+i), h*32+d] = softmax(q k^T) v per head; q (npairs*nq,256), k/v (npairs*512,256), all DEVICE, ld 256. */
 int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const float* v_dev, float* out_dev,
                         int nq, int npairs);
-/* bring-up switch for the shared-memory matrix descriptors (bit0: swap LBO/SBO). */
+/* reserved bring-up switch. */
 void cotr_debug_set_variant(int variant);
 /* debug timeline of the tcgen05 GEMM: DEVICE buffer of 64 int64 per CTA receiving clock64() deltas of the pipeline
  * events of every following GEMM launch (NULL switches it off).  Slot layout: tools/bringup.py::gemm_timeline. */
