@@ -42,6 +42,7 @@ _PROTOTYPES = {
     "cotr_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "cotr_set_graph_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cotr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "cotr_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
     "cotr_profile_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -163,6 +164,9 @@ class NativeModel:
         check(lib().cotr_forward_host(self.handle, ctypes.c_void_p(img_np.ctypes.data), ctypes.c_void_p(queries_np.ctypes.data),
                                       B, Q, ctypes.c_void_p(out_np.ctypes.data)), "cotr_forward_host")
         return out_np
+
+    def set_graph_mode(self, enabled):
+        check(lib().cotr_set_graph_mode(self.handle, int(bool(enabled))), "cotr_set_graph_mode")
 
     def set_gemm_path(self, path):
         check(lib().cotr_set_gemm_path(self.handle, int(path)), "cotr_set_gemm_path")

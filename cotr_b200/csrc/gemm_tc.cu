@@ -9,18 +9,20 @@
 // several TMEM accumulators and the small hi*lo / lo*hi products onto a separate one; the epilogue adds them up with
 // fp32 round-to-nearest.
 //
-// Data movement per CTA (one 128 x BN output tile, K walked in chunks of 64):
-//   * weights: pre-split, pre-tiled in HBM at model creation (tc_pack_weight) into 64-row x 64-k blocks that ARE the
-//     UMMA canonical shared-memory image, so a pipeline stage is BN/64 contiguous 16 KB bulk-TMA copies
-//     (cp.async.bulk -> UBLKCP) completing on an mbarrier;
+// Data movement per CTA (one 128 x BN output tile, K walked in chunks of 64).  Both operands sit in shared memory in
+// the SWIZZLE_128B K-major layout (128-byte rows, 16-byte chunks XOR-swizzled by row % 8):
+//   * weights: pre-split, pre-swizzled in HBM at model creation (tc_pack_weight) as [k chunk][plane][row][128 B], so a
+//     pipeline stage is two contiguous bulk-TMA copies (cp.async.bulk -> UBLKCP, one per plane) completing on an mbarrier;
 //   * activations: already split16 in HBM (the producer's epilogue split them), so warps 0-3 stage the A tile with
-//     asynchronous 16-byte copies (cp.async -> LDGSTS, zero-filled for im2col padding / row tails) whose completion
-//     arrives on the stage's mbarrier (cp.async.mbarrier.arrive.noinc) - no registers, no conversion, up to kStages
-//     chunks in flight.  Only the 7x7 stem reads the caller's fp32 canvas and converts in registers;
-//   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma (N = 64 atoms) and owns TMEM;
-//   * warps 0-3 then run the epilogue out of TMEM: bias / constant add-matrix / residual / ReLU, or the fused
-//     residual + LayerNorm over the full 256-wide row (each thread owns one row, so no cross-thread reduction), and
-//     write split16 (optionally with the value-projection blocks transposed for the attention kernels).
+//     asynchronous 16-byte copies (cp.async -> LDGSTS, zero-filled for im2col padding / row tails; 8 lanes cover one
+//     128-byte row on both sides: coalesced reads, conflict-free writes) whose completion arrives on the stage's
+//     mbarrier (cp.async.mbarrier.arrive.noinc) - no registers, no conversion, up to kStages chunks in flight.  Only
+//     the 7x7 stem reads the caller's fp32 canvas and converts in registers;
+//   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma (N = BN) and owns TMEM;
+//   * warps 0-3 then run the epilogue out of TMEM (software pipelined: the global operands of chunk c+1 are in flight
+//     while chunk c is combined): bias / constant add-matrix / residual / ReLU, or the fused residual + LayerNorm over
+//     the full 256-wide row (each thread owns one row, so no cross-thread reduction), and write split16 (optionally
+//     with the value-projection blocks transposed for the attention kernels).
 // The kernel is templated on the A-operand addressing mode so that each instantiation carries exactly one loader
 // (an earlier all-modes-in-one kernel was ~30k SASS instructions and instruction-cache bound, profiles/r01_*).
 #include <cmath>
@@ -32,7 +34,7 @@
 
 namespace cotr {
 
-int g_tc_variant = 0;                   // bring-up switch (unused bits reserved)
+int g_tc_variant = 0;                   // bring-up switch (reserved)
 long long* g_tc_timestamps = nullptr;   // debug: 64 clock64() stamps per CTA (cotr_debug_set_timestamps), else null
 
 namespace {
@@ -42,30 +44,32 @@ using namespace tc;
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 192;
-constexpr uint32_t kALbo = BM * 16 + 16;       // padded: 8 lanes writing the 8 K-groups of one row hit 32 distinct banks
-constexpr uint32_t kAPlane = 8 * kALbo;        // one fp16 plane (hi or lo) of the 128 x 64 A tile
-constexpr uint32_t kSbo = 128;                 // 8 rows x 16 bytes
+constexpr uint32_t kAPlane = BM * 128;         // one fp16 plane (hi or lo) of the 128 x 64 A tile: 128 rows x 128 bytes
 
 enum LoaderMode : int { LD_GATHER = 0, LD_CONV = 1, LD_STEM = 2 };
 
 __host__ __device__ inline int tc_npad(int N) { return N >= 64 ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16; }
-__host__ __device__ inline int tc_block_rows(int N) { return N >= 64 ? 64 : tc_npad(N); }
 
 template <int BN>
 struct Cfg {
-    static constexpr int kNB = BN >= 64 ? 64 : BN;                      // rows of one weight block == MMA N
-    static constexpr int kBlocks = BN / kNB;
-    static constexpr uint32_t kBBlock = 2u * 8u * kNB * 16u;            // [plane][K group][kNB rows][16 B]
-    static constexpr uint32_t kBStage = kBlocks * kBBlock;
-    static constexpr uint32_t kStage = 2 * kAPlane + kBStage;
-    static constexpr int kStagesRaw = (int)((227u * 1024u - 2048u) / kStage);
+    static constexpr uint32_t kBPlane = BN * 128u;                      // BN rows x 128 bytes
+    static constexpr uint32_t kStage = 2 * kAPlane + 2 * kBPlane;
+    static constexpr int kStagesRaw = (int)((227u * 1024u - 3072u) / kStage);
     static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;
     static constexpr int kMainAcc = BN >= 256 ? 1 : (BN >= 128 ? 3 : 4);
     static constexpr uint32_t kAccCols = (kMainAcc + 1) * BN;
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
-    static constexpr uint32_t kSmemBytes = kStages * kStage + 1024;
+    static constexpr uint32_t kSmemBytes = kStages * kStage + 2048;     // + alignment slack + barriers
     static_assert(kStages >= 2, "pipeline needs at least two stages");
     static_assert(kAccCols <= 512, "TMEM has 512 columns");
+    static_assert(kStage % 1024 == 0, "stages must stay 1024-byte aligned for SWIZZLE_128B");
+};
+
+// global operands of one 16-column epilogue chunk, fetched one chunk ahead of their use
+struct EpiOperands {
+    float4 bias[4];
+    float4 add[4];
+    uint4 res_hi[2], res_lo[2];
 };
 
 template <int BN, bool LN, int MODE>
@@ -75,9 +79,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     long long* my_ts = ts ? ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
     const long long t_start = ts ? clock64() : 0;
 #define COTR_TS(slot) do { if (my_ts) my_ts[(slot)] = clock64() - t_start; } while (0)
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* stage_base = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* stage_base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // SWIZZLE_128B needs 1024-byte alignment
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + C::kStages * C::kStage);
     uint64_t* full_a = bars;
     uint64_t* full_b = bars + C::kStages;
     uint64_t* empty = bars + 2 * C::kStages;
@@ -88,6 +93,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int KC = (p.K + BK - 1) / BK;
+    // Accumulator policy.  TMEM reads are the scarce resource of the epilogue (~64 B/cycle/SM measured), the
+    // truncating accumulate costs ~1e-7 relative per chained MMA: short reductions (K < 1024, <= 48 chained MMAs,
+    // < 1e-6 measured) use ONE accumulator for everything; long ones deal the hi*hi products round-robin onto
+    // kMainAcc accumulators and keep the small correction products on their own.
+    const bool merged = p.K < 1024;
+    const int nacc = merged ? 1 : C::kMainAcc;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
@@ -109,11 +120,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         // ================= A producer ===========================================================================
         const int t = threadIdx.x;
         const int kg = t & 7;          // 16-byte K group (8 halves) inside the 64-wide chunk
-        const int rb = t >> 3;         // rows rb, rb+16, ..., rb+112
+        const int rb = t >> 3;         // rows rb, rb+16, ..., rb+112  (row % 8 == rb % 8 for all of them)
         ARow rows[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rows[i] = decode_a_row(p, m0 + rb + 16 * i);
-        const uint32_t dst0 = smem_u32(stage_base) + (uint32_t)kg * kALbo + (uint32_t)rb * 16u;
+        const uint32_t a_off = (uint32_t)rb * 128u + (uint32_t)((kg ^ (rb & 7)) << 4);   // swizzled chunk position
+        const uint32_t dst0 = smem_u32(stage_base) + a_off;
         if (threadIdx.x == 0) COTR_TS(2);
 
 #pragma unroll 1
@@ -144,12 +156,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     }
                     if (!ok) off = 0;                            // src-size 0 -> 16 bytes of zeros, address unused
                     const uint32_t bytes = ok ? 16u : 0u;
-                    cp_async16(dst + i * 256, p.a.hi + off, bytes);
-                    cp_async16(dst + kAPlane + i * 256, p.a.lo + off, bytes);
+                    cp_async16(dst + i * 2048, p.a.hi + off, bytes);                  // 16 rows x 128 bytes further down
+                    cp_async16(dst + kAPlane + i * 2048, p.a.lo + off, bytes);
                 }
                 cp_async_mbar_arrive_noinc(&full_a[s]);
             } else {
-                uint8_t* a_hi = stage_base + (size_t)s * C::kStage + (uint32_t)kg * kALbo + (uint32_t)rb * 16u;
+                uint8_t* a_hi = stage_base + (size_t)s * C::kStage + a_off;
                 uint8_t* a_lo = a_hi + kAPlane;
 #pragma unroll 1
                 for (int i = 0; i < 8; ++i) {
@@ -160,8 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     split_f16x2(v0.z, v0.w, hi.y, lo.y);
                     split_f16x2(v1.x, v1.y, hi.z, lo.z);
                     split_f16x2(v1.z, v1.w, hi.w, lo.w);
-                    *reinterpret_cast<uint4*>(a_hi + i * 256) = hi;
-                    *reinterpret_cast<uint4*>(a_lo + i * 256) = lo;
+                    *reinterpret_cast<uint4*>(a_hi + i * 2048) = hi;
+                    *reinterpret_cast<uint4*>(a_lo + i * 2048) = lo;
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&full_a[s]);
@@ -177,101 +189,131 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         const bool has_res = row_ok && p.res.hi != nullptr;
         const size_t res_off = (size_t)(row_ok ? row : 0) * p.ldr;
         const float acc_scale = p.acc_scale;
-        mbar_wait(accum_full, 0);
-        tcgen05_fence_after();
-        if (threadIdx.x == 0) COTR_TS(20);
+        const bool tail = p.out_f32 != nullptr && (p.N & 15) != 0;      // only the N = 2 prediction head
+        const bool has_bias = p.bias != nullptr && !tail;
 
+        // issue the global loads of the chunk starting at column nb (bias / add-matrix / residual); N % 16 == 0 here
+        auto prefetch = [&](int nb, EpiOperands& o) {
+            if (nb >= p.N || tail) return;
+            if (has_bias) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o.bias[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
+            }
+            if (add_row) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o.add[j] = __ldg(reinterpret_cast<const float4*>(add_row + nb) + j);
+            }
+            if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    o.res_hi[j] = __ldg(reinterpret_cast<const uint4*>(p.res.hi + res_off + nb) + j);
+                    o.res_lo[j] = __ldg(reinterpret_cast<const uint4*>(p.res.lo + res_off + nb) + j);
+                }
+            }
+        };
+        auto apply = [&](const EpiOperands& o, float (&v)[16]) {
+            if (has_bias) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { v[4 * j] += o.bias[j].x; v[4 * j + 1] += o.bias[j].y; v[4 * j + 2] += o.bias[j].z; v[4 * j + 3] += o.bias[j].w; }
+            }
+            if (add_row) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { v[4 * j] += o.add[j].x; v[4 * j + 1] += o.add[j].y; v[4 * j + 2] += o.add[j].z; v[4 * j + 3] += o.add[j].w; }
+            }
+            if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t h[4] = {o.res_hi[j].x, o.res_hi[j].y, o.res_hi[j].z, o.res_hi[j].w};
+                    const uint32_t l[4] = {o.res_lo[j].x, o.res_lo[j].y, o.res_lo[j].z, o.res_lo[j].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = join_f16x2(h[q], l[q]);
+                        v[8 * j + 2 * q] += f.x;
+                        v[8 * j + 2 * q + 1] += f.y;
+                    }
+                }
+            }
+        };
         // v[0..15] = acc_scale * (sum over all accumulators of columns [c, c+16)); all TMEM loads of the chunk are
         // issued back to back and waited for once.
         auto load_acc = [&](int c, float (&v)[16]) {
             uint32_t r[C::kMainAcc + 1][16];
             __syncwarp();
+            tmem_ld16_issue(trow + c, r[0]);
+            if (!merged) {                              // warp-uniform
 #pragma unroll
-            for (int a = 0; a <= C::kMainAcc; ++a) tmem_ld16_issue(trow + a * BN + c, r[a]);
+                for (int a = 1; a <= C::kMainAcc; ++a) tmem_ld16_issue(trow + a * BN + c, r[a]);
+            }
+            tmem_ld16_fence(r[0]);
+            if (!merged) {
 #pragma unroll
-            for (int a = 0; a <= C::kMainAcc; ++a) tmem_ld16_fence(r[a]);
+                for (int a = 1; a <= C::kMainAcc; ++a) tmem_ld16_fence(r[a]);
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 float x = __uint_as_float(r[0][j]);
+                if (!merged) {
 #pragma unroll
-                for (int a = 1; a <= C::kMainAcc; ++a) x += __uint_as_float(r[a][j]);
+                    for (int a = 1; a <= C::kMainAcc; ++a) x += __uint_as_float(r[a][j]);
+                }
                 v[j] = x * acc_scale;
             }
         };
-        // v += bias / add-matrix / residual for columns [nb, nb+16) (N % 16 == 0 whenever these are present)
-        auto add_operands = [&](int nb, float (&v)[16]) {
-            if (p.bias) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                    v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
-                }
-            }
-            if (add_row) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(add_row + nb + j));
-                    v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
-                }
-            }
-            if (has_res) {
-                float r8[8];
-                load8_split(p.res, res_off + nb, r8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += r8[j];
-                load8_split(p.res, res_off + nb + 8, r8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[8 + j] += r8[j];
-            }
-        };
+
+        EpiOperands ops_cur, ops_nxt;
+        prefetch(LN ? 0 : n0, ops_cur);            // in flight while the last MMAs drain
+        mbar_wait(accum_full, 0);
+        tcgen05_fence_after();
+        if (threadIdx.x == 0) COTR_TS(20);
 
         if constexpr (!LN) {
-            const bool tail = p.out_f32 != nullptr && (p.N & 15) != 0;      // only the N = 2 prediction head
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
+                const int nb = n0 + c;
+                if (c + 16 < BN) prefetch(nb + 16, ops_nxt);
                 float v[16];
                 load_acc(c, v);
-                const int nb = n0 + c;
-                if (!row_ok || nb >= p.N) continue;
-                if (!tail) {
-                    add_operands(nb, v);
-                } else {
+                if (row_ok && nb < p.N) {
+                    if (!tail) {
+                        apply(ops_cur, v);
+                    } else {
 #pragma unroll 1
-                    for (int j = 0; j < 16 && nb + j < p.N; ++j)
-                        if (p.bias) v[j] += __ldg(p.bias + nb + j);
-                }
-                if (p.relu) {
+                        for (int j = 0; j < 16 && nb + j < p.N; ++j)
+                            if (p.bias) v[j] += __ldg(p.bias + nb + j);
+                    }
+                    if (p.relu) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    store16(p, row, nb, v);
                 }
-                store16(p, row, nb, v);
+                ops_cur = ops_nxt;
             }
         } else {
-            // fused residual + LayerNorm (eps 1e-5, biased variance) over the 256 columns this thread owns
-            float sum = 0.f;
+            // fused residual + LayerNorm (eps 1e-5, biased variance) over the 256 columns this thread owns.  One pass
+            // over the accumulators: sum and shifted sum of squares (shift = the row's first value, so the
+            // E[(x-s)^2] - (mean-s)^2 form does not cancel), values parked back in TMEM for the normalisation pass.
+            float sum = 0.f, sq = 0.f, shift = 0.f;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
+                if (c + 16 < BN) prefetch(c + 16, ops_nxt);
                 float v[16];
                 load_acc(c, v);
-                if (row_ok) add_operands(c, v);
+                apply(ops_cur, v);
+                if (c == 0) shift = v[0];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) sum += v[j];
+                for (int j = 0; j < 16; ++j) {
+                    sum += v[j];
+                    const float d = v[j] - shift;
+                    sq = fmaf(d, d, sq);
+                }
                 tmem_st16(trow + c, v);
+                ops_cur = ops_nxt;
             }
             tmem_st_wait();
             const float mean = sum * (1.f / 256.f);
-            float sq = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                float v[16];
-                __syncwarp();
-                tmem_ld16(trow + c, v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float d = v[j] - mean;
-                    sq = fmaf(d, d, sq);
-                }
-            }
+            const float dm = mean - shift;
+            sq = fmaxf(sq * (1.f / 256.f) - dm * dm, 0.f) * 256.f;
             const float rstd = 1.f / sqrtf(sq * (1.f / 256.f) + 1e-5f);
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
@@ -293,23 +335,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         }
         if (threadIdx.x == 0) COTR_TS(21);
     } else if (warp == 4) {
-        // ================= weight producer: bulk TMA of the pre-tiled fp16 hi/lo image ==========================
+        // ================= weight producer: bulk TMA of the pre-swizzled fp16 hi/lo image ========================
         if (lane == 0) {
             const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.Wtc);
-            const int blocks_total = npad / C::kNB;
-            const int blk0 = n0 / C::kNB;
 #pragma unroll 1
             for (int it = 0; it < KC; ++it) {
                 const int s = it % C::kStages;
                 const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_b[s], C::kBStage);
+                mbar_arrive_expect_tx(&full_b[s], 2u * C::kBPlane);
                 uint8_t* b_dst = stage_base + (size_t)s * C::kStage + 2 * kAPlane;
-                // image: [k chunk][64-row block][plane][K group][64 rows][16 bytes]; the blocks of one tile are adjacent
-                const uint8_t* src = wimg + ((size_t)it * blocks_total + blk0) * C::kBBlock;
-#pragma unroll
-                for (int j = 0; j < C::kBlocks; ++j)
-                    tma_bulk_g2s(b_dst + (size_t)j * C::kBBlock, src + (size_t)j * C::kBBlock, C::kBBlock, &full_b[s]);
+                // image: [k chunk][plane][npad rows][128 bytes]; the BN rows of this tile are contiguous per plane
+                const uint8_t* src = wimg + (((size_t)it * 2) * npad + n0) * 128;
+                tma_bulk_g2s(b_dst, src, C::kBPlane, &full_b[s]);
+                tma_bulk_g2s(b_dst + C::kBPlane, src + (size_t)npad * 128, C::kBPlane, &full_b[s]);
                 if (it < 8) COTR_TS(44 + it);
             }
         }
@@ -317,10 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     } else {
         // ================= MMA issuer ===========================================================================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16_f32(BM, C::kNB);
-            constexpr uint32_t b_lbo = C::kNB * 16;
-            constexpr uint32_t b_plane = 8 * b_lbo;
-            const uint32_t hi_word = desc_hi(kSbo);
+            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
+            const uint32_t hi_word = desc_hi_sw128();
             const uint32_t corr_col = tmem_base + (uint32_t)C::kMainAcc * BN;
 #pragma unroll 1
             for (int it = 0; it < KC; ++it) {
@@ -331,23 +368,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 mbar_wait(&full_b[s], ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(stage_base + (size_t)s * C::kStage);
-                // descriptor low words of the first K step; later K steps / planes / blocks only add to the address field
-                const uint32_t a_hi_lo = desc_lo(a_addr, kALbo);
-                const uint32_t b_hi_lo = desc_lo(a_addr + 2 * kAPlane, b_lbo);
+                const uint32_t a_h0 = desc_lo_sw128(a_addr);
+                const uint32_t b_h0 = desc_lo_sw128(a_addr + 2 * kAPlane);
 #pragma unroll
                 for (int ks = 0; ks < BK / 16; ++ks) {
                     const int g = it * (BK / 16) + ks;                       // global K step
-                    const uint32_t a_h = a_hi_lo + ((ks * 2 * kALbo) >> 4);
-                    const uint32_t a_l = a_h + (kAPlane >> 4);
-                    const uint64_t dah = make_desc(a_h, hi_word), dal = make_desc(a_l, hi_word);
-                    const uint32_t main_col = tmem_base + (uint32_t)(g % C::kMainAcc) * BN;
-#pragma unroll
-                    for (int j = 0; j < C::kBlocks; ++j) {
-                        const uint32_t b_h = b_hi_lo + ((j * C::kBBlock + ks * 2 * b_lbo) >> 4);
-                        const uint64_t dbh = make_desc(b_h, hi_word), dbl = make_desc(b_h + (b_plane >> 4), hi_word);
-                        umma_f16_ss(corr_col + j * C::kNB, dal, dbh, idesc, g != 0);
-                        umma_f16_ss(corr_col + j * C::kNB, dah, dbl, idesc, true);
-                        umma_f16_ss(main_col + j * C::kNB, dah, dbh, idesc, g >= C::kMainAcc);
+                    // a K step of 16 halves = 32 bytes inside the 128-byte swizzle atom: +2 in the address field
+                    const uint64_t dah = make_desc(a_h0 + 2 * ks, hi_word);
+                    const uint64_t dal = make_desc(a_h0 + (kAPlane >> 4) + 2 * ks, hi_word);
+                    const uint64_t dbh = make_desc(b_h0 + 2 * ks, hi_word);
+                    const uint64_t dbl = make_desc(b_h0 + (C::kBPlane >> 4) + 2 * ks, hi_word);
+                    if (merged) {
+                        umma_f16_ss(tmem_base, dal, dbh, idesc, g != 0);
+                        umma_f16_ss(tmem_base, dah, dbl, idesc, true);
+                        umma_f16_ss(tmem_base, dah, dbh, idesc, true);
+                    } else {
+                        const uint32_t main_col = tmem_base + (uint32_t)(g % nacc) * BN;
+                        umma_f16_ss(corr_col, dal, dbh, idesc, g != 0);
+                        umma_f16_ss(corr_col, dah, dbl, idesc, true);
+                        umma_f16_ss(main_col, dah, dbh, idesc, g >= nacc);
                     }
                 }
                 umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
@@ -435,16 +474,14 @@ inline float f16_to_f32(uint16_t h) {
 
 size_t tc_weight_bytes(int N, int K) {
     const size_t kc = (K + BK - 1) / BK;
-    return kc * 16 * (size_t)tc_npad(N) * 16;
+    return kc * 2 * (size_t)tc_npad(N) * 128;
 }
 
-// Image layout: [k chunk (64)][row block (64 rows; 16 when N < 64)][plane: hi, lo][K group (8 halves)][row][8 halves],
-// zero padded in N and K.  The matrix is multiplied by 2^e, e chosen so that max|w| * 2^e lies in [2^12, 2^13);
-// returns 2^-e for the epilogue.
+// Image layout: [k chunk (64)][plane: hi, lo][row (npad)][128 bytes = 8 chunks of 8 halves], chunk c of row r stored
+// at chunk position c ^ (r % 8) (SWIZZLE_128B); zero padded in N and K.  The matrix is multiplied by 2^e, e chosen so
+// that max|w| * 2^e lies in [2^12, 2^13); returns 2^-e for the epilogue.
 float tc_pack_weight(const float* w, int N, int K, void* dst_host) {
     const int npad = tc_npad(N);
-    const int nb = tc_block_rows(N);
-    const int blocks = npad / nb;
     const int kc_n = (K + BK - 1) / BK;
     float amax = 0.f;
     for (size_t i = 0; i < (size_t)N * K; ++i) amax = fmaxf(amax, fabsf(w[i]));
@@ -457,19 +494,17 @@ float tc_pack_weight(const float* w, int N, int K, void* dst_host) {
     const float scale = ldexpf(1.f, e);
     uint16_t* out = reinterpret_cast<uint16_t*>(dst_host);
     for (int kc = 0; kc < kc_n; ++kc)
-        for (int b = 0; b < blocks; ++b)
-            for (int kg = 0; kg < 8; ++kg)
-                for (int r = 0; r < nb; ++r)
-                    for (int el = 0; el < 8; ++el) {
-                        const int n = b * nb + r;
-                        const int k = kc * BK + kg * 8 + el;
-                        const float x = (n < N && k < K) ? w[(size_t)n * K + k] * scale : 0.f;
-                        const uint16_t hi = f32_to_f16_rn(x);
-                        const uint16_t lo = f32_to_f16_rn(x - f16_to_f32(hi));
-                        const size_t blk = ((size_t)kc * blocks + b) * 2;
-                        out[(((blk + 0) * 8 + kg) * nb + r) * 8 + el] = hi;
-                        out[(((blk + 1) * 8 + kg) * nb + r) * 8 + el] = lo;
-                    }
+        for (int r = 0; r < npad; ++r)
+            for (int c = 0; c < 8; ++c)
+                for (int el = 0; el < 8; ++el) {
+                    const int k = kc * BK + c * 8 + el;
+                    const float x = (r < N && k < K) ? w[(size_t)r * K + k] * scale : 0.f;
+                    const uint16_t hi = f32_to_f16_rn(x);
+                    const uint16_t lo = f32_to_f16_rn(x - f16_to_f32(hi));
+                    const size_t pos = (size_t)r * 64 + (size_t)((c ^ (r & 7)) * 8) + el;      // in halves
+                    out[((size_t)kc * 2 + 0) * npad * 64 + pos] = hi;
+                    out[((size_t)kc * 2 + 1) * npad * 64 + pos] = lo;
+                }
     return ldexpf(1.f, -e);
 }
 

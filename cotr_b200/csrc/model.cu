@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -117,6 +118,11 @@ struct cotr_model {
     cotr::Split16 last_mem = cotr::kNoSplit;
     int last_pairs = 0, last_rows = 0;
     // per-launch profiler (cotr_profile_begin / cotr_profile_end): CUDA event pairs on the launching stream
+    // CUDA-graph replay of cotr_forward, one executable graph per (B, Q) shape (captured on the second call)
+    bool graph_mode = true;
+    std::map<long long, cudaGraphExec_t> graphs;
+    std::map<long long, int> graph_launches;
+    std::set<long long> shapes_seen;
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_events;      // 2 per record
     std::vector<cotr_launch_record> prof_records;
@@ -764,6 +770,7 @@ void cotr_destroy(cotr_model* m) {
     float** fbufs[] = {&w.ln_tmp, &w.dln_tmp, &w.img_stage, &w.q_stage, &w.pred_stage};
     for (float** b : fbufs) ws_free_f32(b);
     if (m->host_stream) cudaStreamDestroy(m->host_stream);
+    for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
     for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
     delete m;
 }
@@ -802,24 +809,9 @@ int cotr_decode(cotr_model* m, const cotr_context* ctx, const float* queries_dev
     return decode_impl(m, ctx, queries_dev, B, Q, pred_dev, (cudaStream_t)cuda_stream);
 }
 
-int cotr_forward(cotr_model* m, const float* img_dev, const float* queries_dev, int B, int Q, float* pred_dev, void* cuda_stream) {
-    COTR_CHECK(m && img_dev && (Q == 0 || (queries_dev && pred_dev)), "cotr_forward: null argument");
-    COTR_CHECK(B >= 1, "cotr_forward: B must be >= 1");
-    if (m->own_ctx->max_pairs < B) {
-        COTR_CHECK_CUDA(cudaDeviceSynchronize());
-        cotr_context_destroy(m->own_ctx);
-        m->own_ctx = nullptr;
-        if (cotr_context_create(m, B, &m->own_ctx)) return 1;
-    }
-    m->launches = 0;
-    if (encode_impl(m, img_dev, B, m->own_ctx, (cudaStream_t)cuda_stream)) return 1;
-    return decode_impl(m, m->own_ctx, queries_dev, B, Q, pred_dev, (cudaStream_t)cuda_stream);
-}
+namespace {
 
-int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries_host, int B, int Q, float* pred_host) {
-    COTR_CHECK(m && img_host && (Q == 0 || (queries_host && pred_host)), "cotr_forward_host: null argument");
-    COTR_CHECK(B >= 1, "cotr_forward_host: B must be >= 1");
-    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+int ensure_stage(cotr_model* m, int B, int Q) {
     Workspace& w = m->ws;
     const size_t img_elems = (size_t)B * 3 * COTR_CANVAS_H * COTR_CANVAS_W;
     const size_t q_elems = (size_t)B * Q * 2;
@@ -832,15 +824,102 @@ int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries
     if (q_elems > w.q_stage_elems) {
         COTR_CHECK_CUDA(cudaDeviceSynchronize());
         ws_free_f32(&w.q_stage); ws_free_f32(&w.pred_stage);
-        if (ws_alloc_f32(&w.q_stage, q_elems) || ws_alloc_f32(&w.pred_stage, q_elems)) return 1;
+        if (ws_alloc_f32(&w.q_stage, q_elems ? q_elems : 2) || ws_alloc_f32(&w.pred_stage, q_elems ? q_elems : 2)) return 1;
         w.q_stage_elems = q_elems;
     }
+    return 0;
+}
+
+int forward_eager(cotr_model* m, const float* img, const float* queries, int B, int Q, float* pred, cudaStream_t s) {
+    if (m->own_ctx->max_pairs < B) {
+        COTR_CHECK_CUDA(cudaDeviceSynchronize());
+        cotr_context_destroy(m->own_ctx);
+        m->own_ctx = nullptr;
+        if (cotr_context_create(m, B, &m->own_ctx)) return 1;
+    }
+    m->launches = 0;
+    if (encode_impl(m, img, B, m->own_ctx, s)) return 1;
+    return decode_impl(m, m->own_ctx, queries, B, Q, pred, s);
+}
+
+// Forward on the staging buffers (img_stage, q_stage -> pred_stage): graph replay when a graph exists for the shape.
+int forward_staged(cotr_model* m, int B, int Q, cudaStream_t s) {
+    Workspace& w = m->ws;
+    const bool graphable = m->graph_mode && !m->prof_on && g_tc_timestamps == nullptr;
+    const long long key = ((long long)B << 32) | (unsigned)Q;
+    if (graphable) {
+        auto it = m->graphs.find(key);
+        if (it != m->graphs.end()) {
+            COTR_CHECK_CUDA(cudaGraphLaunch(it->second, s));
+            m->launches = m->graph_launches[key];
+            return 0;
+        }
+        if (m->shapes_seen.count(key) && m->graphs.size() < 256) {
+            // second call with this shape: workspace, contexts and kernel attributes are in place -> capture
+            cudaGraph_t graph = nullptr;
+            COTR_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = forward_eager(m, w.img_stage, w.q_stage, B, Q, w.pred_stage, s);
+            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (rc || e != cudaSuccess || graph == nullptr) {
+                if (graph) cudaGraphDestroy(graph);
+                if (!rc) set_error("cotr_forward: stream capture failed: %s", cudaGetErrorString(e));
+                return 1;
+            }
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            COTR_CHECK(ei == cudaSuccess, "cotr_forward: cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+            m->graphs[key] = exec;
+            m->graph_launches[key] = m->launches;
+            COTR_CHECK_CUDA(cudaGraphLaunch(exec, s));
+            return 0;
+        }
+        m->shapes_seen.insert(key);
+    }
+    return forward_eager(m, w.img_stage, w.q_stage, B, Q, w.pred_stage, s);
+}
+
+}  // namespace
+
+int cotr_forward(cotr_model* m, const float* img_dev, const float* queries_dev, int B, int Q, float* pred_dev, void* cuda_stream) {
+    COTR_CHECK(m && img_dev && (Q == 0 || (queries_dev && pred_dev)), "cotr_forward: null argument");
+    COTR_CHECK(B >= 1 && Q >= 0, "cotr_forward: B must be >= 1 and Q >= 0");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const bool graphable = m->graph_mode && !m->prof_on && g_tc_timestamps == nullptr && Q > 0;
+    if (!graphable) return forward_eager(m, img_dev, queries_dev, B, Q, pred_dev, s);
+    // graph replay needs fixed addresses: go through the staging buffers (two small device-to-device copies in, one out)
+    if (ensure_stage(m, B, Q)) return 1;
+    Workspace& w = m->ws;
+    const size_t img_bytes = (size_t)B * 3 * COTR_CANVAS_H * COTR_CANVAS_W * sizeof(float), q_bytes = (size_t)B * Q * 2 * sizeof(float);
+    COTR_CHECK_CUDA(cudaMemcpyAsync(w.img_stage, img_dev, img_bytes, cudaMemcpyDeviceToDevice, s));
+    COTR_CHECK_CUDA(cudaMemcpyAsync(w.q_stage, queries_dev, q_bytes, cudaMemcpyDeviceToDevice, s));
+    if (forward_staged(m, B, Q, s)) return 1;
+    COTR_CHECK_CUDA(cudaMemcpyAsync(pred_dev, w.pred_stage, q_bytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries_host, int B, int Q, float* pred_host) {
+    COTR_CHECK(m && img_host && (Q == 0 || (queries_host && pred_host)), "cotr_forward_host: null argument");
+    COTR_CHECK(B >= 1 && Q >= 0, "cotr_forward_host: B must be >= 1 and Q >= 0");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    if (ensure_stage(m, B, Q)) return 1;
+    Workspace& w = m->ws;
+    const size_t img_bytes = (size_t)B * 3 * COTR_CANVAS_H * COTR_CANVAS_W * sizeof(float), q_bytes = (size_t)B * Q * 2 * sizeof(float);
     cudaStream_t s = m->host_stream;
-    COTR_CHECK_CUDA(cudaMemcpyAsync(w.img_stage, img_host, img_elems * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (q_elems) COTR_CHECK_CUDA(cudaMemcpyAsync(w.q_stage, queries_host, q_elems * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (cotr_forward(m, w.img_stage, w.q_stage, B, Q, w.pred_stage, s)) return 1;
-    if (q_elems) COTR_CHECK_CUDA(cudaMemcpyAsync(pred_host, w.pred_stage, q_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    COTR_CHECK_CUDA(cudaMemcpyAsync(w.img_stage, img_host, img_bytes, cudaMemcpyHostToDevice, s));
+    if (q_bytes) COTR_CHECK_CUDA(cudaMemcpyAsync(w.q_stage, queries_host, q_bytes, cudaMemcpyHostToDevice, s));
+    if (Q > 0) {
+        if (forward_staged(m, B, Q, s)) return 1;
+        COTR_CHECK_CUDA(cudaMemcpyAsync(pred_host, w.pred_stage, q_bytes, cudaMemcpyDeviceToHost, s));
+    }
     COTR_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int cotr_set_graph_mode(cotr_model* m, int enabled) {
+    COTR_CHECK(m != nullptr, "cotr_set_graph_mode: null model");
+    m->graph_mode = enabled != 0;
     return 0;
 }
 
@@ -905,6 +984,14 @@ int64_t cotr_debug_read(cotr_model* m, const char* name, float* out_host, int64_
 
 int cotr_set_gemm_path(cotr_model* m, int path) {
     COTR_CHECK(m && (path == 0 || path == 1), "cotr_set_gemm_path: path must be 0 (tcgen05) or 1 (fp32 SIMT)");
+    if (m->gemm_path != path) {          // captured graphs embed the kernels of the old path
+        cudaSetDevice(m->device);
+        cudaDeviceSynchronize();
+        for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+        m->graphs.clear();
+        m->graph_launches.clear();
+        m->shapes_seen.clear();
+    }
     m->gemm_path = path;
     return 0;
 }

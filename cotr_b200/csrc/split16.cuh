@@ -4,18 +4,20 @@
 
 namespace cotr {
 
-// x ~= hi + lo with ~22 mantissa bits.  |x| is clamped to the fp16 range for hi (lo then carries up to another
-// 65504); below 2^-3 the lo term is an fp16 subnormal, i.e. the absolute error floors at ~3e-8.
+// x ~= hi + lo with ~22 mantissa bits.  Both terms saturate at the fp16 range, so the format represents |x| up to
+// 131008 and clamps beyond (never inf / NaN); below 2^-3 the lo term is an fp16 subnormal, i.e. the absolute error
+// floors at ~3e-8.
+__device__ __forceinline__ float sat16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    const __half2 h = __floats2half2_rn(sat16(a), sat16(b));
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    const __half2 l = __floats2half2_rn(sat16(a - hf.x), sat16(b - hf.y));
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void split_f16(float a, __half& hi, __half& lo) {
-    hi = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f));
-    lo = __float2half_rn(a - __half2float(hi));
+    hi = __float2half_rn(sat16(a));
+    lo = __float2half_rn(sat16(a - __half2float(hi)));
 }
 __device__ __forceinline__ float2 join_f16x2(uint32_t hi, uint32_t lo) {
     const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));

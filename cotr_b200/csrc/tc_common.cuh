@@ -87,6 +87,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return make_desc(desc_lo(smem_addr, lbo_bytes), desc_hi(sbo_bytes));
 }
 
+// SWIZZLE_128B K-major operand tile: rows of 128 bytes (64 halves = one K chunk), 8-row groups 1024 bytes apart, the
+// 16-byte chunk c of row r stored at chunk position c ^ (r % 8) (tile base 1024-byte aligned).  LBO is not used by the
+// hardware in this mode (encoded as 1 like CUTLASS), SBO = 1024, layout_type = 2.  A K step of 16 halves advances the
+// start address by 32 bytes inside the swizzle atom.
+__device__ __forceinline__ uint32_t desc_hi_sw128() { return (1024u >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+
 // Instruction descriptor for kind::f16: FP16 x FP16 -> FP32 (a_format = b_format = 0), both operands K-major, dense.
 __host__ __device__ constexpr uint32_t make_idesc_f16_f32(int M, int N) {
     return (1u << 4)                      // c_format = F32

@@ -79,6 +79,10 @@ int cotr_forward(cotr_model* m, const float* img_dev, const float* queries_dev, 
 int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries_host, int B, int Q,
                       float* pred_host);
 
+/* cotr_forward / cotr_forward_host replay a CUDA graph per (B,Q) shape (captured on the second call with that shape;
+ * inputs / outputs pass through internal staging buffers so the graph's addresses stay fixed).  0 disables it. */
+int cotr_set_graph_mode(cotr_model* m, int enabled);
+
 /* Bytes of device workspace a (B,Q) call needs (activations only, excluding weights and contexts). */
 size_t cotr_workspace_bytes(int B, int Q);
 
