@@ -56,8 +56,19 @@ struct Cfg {
     static constexpr uint32_t kStage = 2 * kAPlane + 2 * kBPlane;
     static constexpr int kStagesRaw = (int)((227u * 1024u - 3072u) / kStage);
     static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;
-    static constexpr int kMainAcc = BN >= 256 ? 1 : (BN >= 128 ? 3 : 4);
-    static constexpr uint32_t kAccCols = (kMainAcc + 1) * BN;
+    // TMEM accumulator slots of BN columns each: kMain slots take the hi*hi products round-robin over K steps (the
+    // truncating accumulate is a systematic bias that grows with the chain length and adds up across layers), kCorr
+    // slots take the small lo*hi / hi*lo products.  Consecutive MMAs never chain on the same accumulator where TMEM
+    // allows (a chained MMA waits ~110 cycles for its predecessor).
+    static constexpr int kMain = BN >= 256 ? 1 : (BN >= 128 ? 2 : 4);   // BN = 16 / 32 / 64: 4
+    static constexpr int kCorr = BN >= 256 ? 1 : 2;
+    static constexpr int kSlots = kMain + kCorr;
+    static constexpr uint32_t kAccCols = kSlots * BN;
+    // epilogue staging (re-uses the pipeline stages): per warp 2 planes x 32 rows, row pitch padded by 16 bytes
+    static constexpr uint32_t kOutPitch = BN * 2u + 16u;
+    static constexpr uint32_t kWarpStaging = 2u * 32u * kOutPitch;
+    static constexpr int kChunksN = BN / 16;
+    static constexpr int kRing = kChunksN < 4 ? kChunksN : 4;          // epilogue operand prefetch depth
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
     static constexpr uint32_t kSmemBytes = kStages * kStage + 2048;     // + alignment slack + barriers
     static_assert(kStages >= 2, "pipeline needs at least two stages");
@@ -93,12 +104,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int KC = (p.K + BK - 1) / BK;
-    // Accumulator policy.  TMEM reads are the scarce resource of the epilogue (~64 B/cycle/SM measured), the
-    // truncating accumulate costs ~1e-7 relative per chained MMA: short reductions (K < 1024, <= 48 chained MMAs,
-    // < 1e-6 measured) use ONE accumulator for everything; long ones deal the hi*hi products round-robin onto
-    // kMainAcc accumulators and keep the small correction products on their own.
-    const bool merged = p.K < 1024;
-    const int nacc = merged ? 1 : C::kMainAcc;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
@@ -237,70 +242,122 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         // v[0..15] = acc_scale * (sum over all accumulators of columns [c, c+16)); all TMEM loads of the chunk are
         // issued back to back and waited for once.
         auto load_acc = [&](int c, float (&v)[16]) {
-            uint32_t r[C::kMainAcc + 1][16];
+            uint32_t r[C::kSlots][16];
             __syncwarp();
-            tmem_ld16_issue(trow + c, r[0]);
-            if (!merged) {                              // warp-uniform
 #pragma unroll
-                for (int a = 1; a <= C::kMainAcc; ++a) tmem_ld16_issue(trow + a * BN + c, r[a]);
-            }
-            tmem_ld16_fence(r[0]);
-            if (!merged) {
+            for (int a = 0; a < C::kSlots; ++a) tmem_ld16_issue(trow + a * BN + c, r[a]);
 #pragma unroll
-                for (int a = 1; a <= C::kMainAcc; ++a) tmem_ld16_fence(r[a]);
-            }
+            for (int a = 0; a < C::kSlots; ++a) tmem_ld16_fence(r[a]);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(r[0][j]);
-                if (!merged) {
+                float x = __uint_as_float(r[C::kMain][j]);                          // small terms first
+                if (C::kCorr == 2) x += __uint_as_float(r[C::kMain + 1][j]);
+                float y = __uint_as_float(r[0][j]);
 #pragma unroll
-                    for (int a = 1; a <= C::kMainAcc; ++a) x += __uint_as_float(r[a][j]);
-                }
-                v[j] = x * acc_scale;
+                for (int a = 1; a < C::kMain; ++a) y += __uint_as_float(r[a][j]);
+                v[j] = (x + y) * acc_scale;
             }
         };
 
-        EpiOperands ops_cur, ops_nxt;
-        prefetch(LN ? 0 : n0, ops_cur);            // in flight while the last MMAs drain
+        // Output path.  split16 row-major tiles are staged in shared memory (the pipeline stages are idle once the
+        // accumulator is complete; each warp stages and drains only its own 32 rows, so a __syncwarp suffices) and
+        // written out as full 128-byte-coalesced rows; a thread-per-row direct store would touch 32 different cache
+        // lines per instruction.  Transposed value blocks and the fp32 prediction head keep the direct path.
+        size_t tile_base = 0;
+        const bool direct = p.out_f32 != nullptr || out_location(p, m0, n0, tile_base);
+        uint8_t* stg = stage_base + (uint32_t)warp * C::kWarpStaging + (uint32_t)lane * C::kOutPitch;
+        auto emit16 = [&](int c, const float (&v)[16]) {          // c = column inside the tile
+            if (direct) {
+                if (row_ok && n0 + c < p.N) store16(p, row, n0 + c, v);
+                return;
+            }
+            uint4 h0, l0, h1, l1;
+            split_f16x2(v[0], v[1], h0.x, l0.x);   split_f16x2(v[2], v[3], h0.y, l0.y);
+            split_f16x2(v[4], v[5], h0.z, l0.z);   split_f16x2(v[6], v[7], h0.w, l0.w);
+            split_f16x2(v[8], v[9], h1.x, l1.x);   split_f16x2(v[10], v[11], h1.y, l1.y);
+            split_f16x2(v[12], v[13], h1.z, l1.z); split_f16x2(v[14], v[15], h1.w, l1.w);
+            uint8_t* d = stg + c * 2;
+            *reinterpret_cast<uint4*>(d) = h0;
+            *reinterpret_cast<uint4*>(d + 16) = h1;
+            *reinterpret_cast<uint4*>(d + 32 * C::kOutPitch) = l0;
+            *reinterpret_cast<uint4*>(d + 32 * C::kOutPitch + 16) = l1;
+        };
+        auto drain = [&]() {
+            if (direct) return;
+            __syncwarp();
+            constexpr int kLanesPerRow = BN * 2 / 16;                     // 16-byte pieces per row of one plane
+            constexpr int kRowsPerPass = kLanesPerRow >= 32 ? 1 : 32 / kLanesPerRow;
+            constexpr int kPiecesPerLane = kLanesPerRow > 32 ? kLanesPerRow / 32 : 1;
+            const uint8_t* wbase = stage_base + (uint32_t)warp * C::kWarpStaging;
+            const int r_in = kLanesPerRow >= 32 ? 0 : lane / kLanesPerRow;
+            const int piece0 = kLanesPerRow >= 32 ? lane : lane % kLanesPerRow;
+#pragma unroll
+            for (int plane = 0; plane < 2; ++plane) {
+                __half* gout = (plane == 0 ? p.out.hi : p.out.lo) + tile_base;     // element (m0, n0 mapped)
+#pragma unroll 4
+                for (int r0 = 0; r0 < 32; r0 += kRowsPerPass) {
+                    const int rr = r0 + r_in;
+                    const int grow_ = m0 + warp * 32 + rr;
+#pragma unroll
+                    for (int q = 0; q < kPiecesPerLane; ++q) {
+                        const int piece = piece0 + q * 32;
+                        const uint4 val = *reinterpret_cast<const uint4*>(wbase + (uint32_t)(plane * 32 + rr) * C::kOutPitch + piece * 16);
+                        if (grow_ < p.M)
+                            *reinterpret_cast<uint4*>(gout + (size_t)(warp * 32 + rr) * p.ldc + piece * 8) = val;
+                    }
+                }
+            }
+        };
+
+        // The loader warps finish issuing their copies several pipeline stages before the last MMA retires: use that
+        // slack to get the epilogue's global operands in flight (kRing chunks deep), then keep the ring full.
+        EpiOperands ops[C::kRing];
+        const int nbase = LN ? 0 : n0;
+#pragma unroll
+        for (int i = 0; i < C::kRing; ++i) prefetch(nbase + 16 * i, ops[i]);
         mbar_wait(accum_full, 0);
         tcgen05_fence_after();
         if (threadIdx.x == 0) COTR_TS(20);
 
         if constexpr (!LN) {
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
+#pragma unroll
+            for (int ci = 0; ci < C::kChunksN; ++ci) {
+                const int c = ci * 16;
                 const int nb = n0 + c;
-                if (c + 16 < BN) prefetch(nb + 16, ops_nxt);
                 float v[16];
                 load_acc(c, v);
-                if (row_ok && nb < p.N) {
-                    if (!tail) {
-                        apply(ops_cur, v);
-                    } else {
+                if (threadIdx.x == 0 && ci < 2) COTR_TS(30 + 4 * ci);
+                if (!tail) {
+                    apply(ops[ci % C::kRing], v);
+                } else {
 #pragma unroll 1
-                        for (int j = 0; j < 16 && nb + j < p.N; ++j)
-                            if (p.bias) v[j] += __ldg(p.bias + nb + j);
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-                    store16(p, row, nb, v);
+                    for (int j = 0; j < 16 && nb + j < p.N; ++j)
+                        if (p.bias) v[j] += __ldg(p.bias + nb + j);
                 }
-                ops_cur = ops_nxt;
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (threadIdx.x == 0 && ci < 2) COTR_TS(31 + 4 * ci);
+                emit16(c, v);
+                if (threadIdx.x == 0 && ci < 2) COTR_TS(32 + 4 * ci);
+                if (ci + C::kRing < C::kChunksN) prefetch(nb + 16 * C::kRing, ops[ci % C::kRing]);
             }
+            if (threadIdx.x == 0) COTR_TS(38);
+            drain();
         } else {
             // fused residual + LayerNorm (eps 1e-5, biased variance) over the 256 columns this thread owns.  One pass
             // over the accumulators: sum and shifted sum of squares (shift = the row's first value, so the
             // E[(x-s)^2] - (mean-s)^2 form does not cancel), values parked back in TMEM for the normalisation pass.
             float sum = 0.f, sq = 0.f, shift = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                if (c + 16 < BN) prefetch(c + 16, ops_nxt);
+#pragma unroll
+            for (int ci = 0; ci < C::kChunksN; ++ci) {
+                const int c = ci * 16;
                 float v[16];
                 load_acc(c, v);
-                apply(ops_cur, v);
-                if (c == 0) shift = v[0];
+                apply(ops[ci % C::kRing], v);
+                if (ci + C::kRing < C::kChunksN) prefetch(c + 16 * C::kRing, ops[ci % C::kRing]);
+                if (ci == 0) shift = v[0];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     sum += v[j];
@@ -308,30 +365,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     sq = fmaf(d, d, sq);
                 }
                 tmem_st16(trow + c, v);
-                ops_cur = ops_nxt;
             }
             tmem_st_wait();
             const float mean = sum * (1.f / 256.f);
             const float dm = mean - shift;
-            sq = fmaxf(sq * (1.f / 256.f) - dm * dm, 0.f) * 256.f;
-            const float rstd = 1.f / sqrtf(sq * (1.f / 256.f) + 1e-5f);
+            const float var = fmaxf(sq * (1.f / 256.f) - dm * dm, 0.f);
+            const float rstd = 1.f / sqrtf(var + 1e-5f);
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                float v[16];
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[2][16];
                 __syncwarp();
-                tmem_ld16(trow + c, v);
-                if (!row_ok) continue;
+                tmem_ld16_issue(trow + c, r[0]);
+                tmem_ld16_issue(trow + c + 16, r[1]);
+                tmem_ld16_fence(r[0]);
+                tmem_ld16_fence(r[1]);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c + j));
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c + j));
-                    v[j] = (v[j] - mean) * rstd * g4.x + b4.x;
-                    v[j + 1] = (v[j + 1] - mean) * rstd * g4.y + b4.y;
-                    v[j + 2] = (v[j + 2] - mean) * rstd * g4.z + b4.z;
-                    v[j + 3] = (v[j + 3] - mean) * rstd * g4.w + b4.w;
+                for (int h = 0; h < 2; ++h) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c + h * 16 + j));
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c + h * 16 + j));
+                        v[j] = (__uint_as_float(r[h][j]) - mean) * rstd * g4.x + b4.x;
+                        v[j + 1] = (__uint_as_float(r[h][j + 1]) - mean) * rstd * g4.y + b4.y;
+                        v[j + 2] = (__uint_as_float(r[h][j + 2]) - mean) * rstd * g4.z + b4.z;
+                        v[j + 3] = (__uint_as_float(r[h][j + 3]) - mean) * rstd * g4.w + b4.w;
+                    }
+                    emit16(c + h * 16, v);
                 }
-                store16(p, row, c, v);
             }
+            drain();
         }
         if (threadIdx.x == 0) COTR_TS(21);
     } else if (warp == 4) {
@@ -358,7 +421,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
             const uint32_t hi_word = desc_hi_sw128();
-            const uint32_t corr_col = tmem_base + (uint32_t)C::kMainAcc * BN;
+            const uint32_t corr_a = tmem_base + (uint32_t)C::kMain * BN;
+            const uint32_t corr_b = tmem_base + (uint32_t)(C::kMain + C::kCorr - 1) * BN;
 #pragma unroll 1
             for (int it = 0; it < KC; ++it) {
                 const int s = it % C::kStages;
@@ -378,16 +442,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     const uint64_t dal = make_desc(a_h0 + (kAPlane >> 4) + 2 * ks, hi_word);
                     const uint64_t dbh = make_desc(b_h0 + 2 * ks, hi_word);
                     const uint64_t dbl = make_desc(b_h0 + (C::kBPlane >> 4) + 2 * ks, hi_word);
-                    if (merged) {
-                        umma_f16_ss(tmem_base, dal, dbh, idesc, g != 0);
-                        umma_f16_ss(tmem_base, dah, dbl, idesc, true);
-                        umma_f16_ss(tmem_base, dah, dbh, idesc, true);
-                    } else {
-                        const uint32_t main_col = tmem_base + (uint32_t)(g % nacc) * BN;
-                        umma_f16_ss(corr_col, dal, dbh, idesc, g != 0);
-                        umma_f16_ss(corr_col, dah, dbl, idesc, true);
-                        umma_f16_ss(main_col, dah, dbh, idesc, g >= nacc);
-                    }
+                    const uint32_t main_col = tmem_base + (uint32_t)(g % C::kMain) * BN;
+                    umma_f16_ss(corr_a, dal, dbh, idesc, g != 0);
+                    umma_f16_ss(main_col, dah, dbh, idesc, g >= C::kMain);
+                    umma_f16_ss(corr_b, dah, dbl, idesc, C::kCorr == 1 ? true : g != 0);
                 }
                 umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
                 if (it < 8) COTR_TS(25 + 2 * it);
@@ -424,7 +482,7 @@ template <int BN, bool LN>
 int launch_mode(const GemmParams& p, cudaStream_t s) {
     const bool gather = (p.a_mode == A_ROWMAJOR || p.a_mode == A_TOKENS);
     if (gather && (p.K & 7) == 0 && (p.lda & 7) == 0) return launch_one<BN, LN, LD_GATHER>(p, s);
-    if constexpr (!LN && BN >= 64) {
+    if constexpr (!LN && BN >= 32) {
         if (p.a_mode == A_CONV_NHWC && (p.C & 63) == 0) return launch_one<BN, LN, LD_CONV>(p, s);
     }
     if constexpr (!LN && BN == 64) {
@@ -523,9 +581,13 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         COTR_CHECK(p.N <= 16, "gemm_tc: N between 17 and 63 is not instantiated");
         return launch_mode<16, false>(p, s);
     }
-    const int mt = (p.M + BM - 1) / BM;
-    if ((p.N % 128) == 0 && (long long)mt * (p.N / 128) >= 120) return launch_mode<128, false>(p, s);
-    return launch_mode<64, false>(p, s);
+    // Tile width: at small batch most GEMMs of this network have a handful of 128-row tiles, so the widest tile
+    // that still yields ~100 CTAs (148 SMs) wins; the narrow tiles trade tensor efficiency for parallelism and a
+    // shorter per-CTA epilogue (the critical path of these latency-bound launches).
+    const long long mt = (p.M + BM - 1) / BM;
+    if ((p.N % 128) == 0 && mt * (p.N / 128) >= 96) return launch_mode<128, false>(p, s);
+    if (mt * ((p.N + 63) / 64) >= 96 || p.a_mode == A_STEM_NCHW || (p.N % 32) != 0) return launch_mode<64, false>(p, s);
+    return launch_mode<32, false>(p, s);
 }
 
 }  // namespace cotr

@@ -286,8 +286,22 @@ GemmParams gemm_base(int M, int N, int K, CSplit16 A, int lda, const float* W, c
 // ln_scratch: fp32 [M][256] staging for the SIMT path (the tensor-core GEMM fuses LayerNorm into its epilogue).
 int run_gemm(const Run& r, GemmParams p, float* ln_scratch) {
     if (r.m->gemm_path == 0) {
-        LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
-        return launch_gemm_tc(p, r.s);
+        // The fused LayerNorm epilogue needs the whole 256-wide row in one CTA (128 x 256 tile): with few rows that is
+        // a handful of CTAs doing a long serial epilogue while the other SMs idle.  Below ~64 row tiles the GEMM runs
+        // with narrow tiles across many SMs and LayerNorm follows as its own (in-place, one warp per row) kernel.
+        const bool defuse = p.ln_gamma != nullptr && (p.M + 127) / 128 < 64;
+        const float* g = p.ln_gamma;
+        const float* b = p.ln_beta;
+        if (defuse) { p.ln_gamma = nullptr; p.ln_beta = nullptr; }
+        {
+            LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
+            if (launch_gemm_tc(p, r.s)) return 1;
+        }
+        if (defuse) {
+            LaunchScope scope(r, K_LAYERNORM, p.M, kDModel, 0);
+            if (launch_layernorm(cs(p.out), g, b, p.out, p.M, r.s)) return 1;
+        }
+        return 0;
     }
     const float* g = p.ln_gamma;
     const float* b = p.ln_beta;
@@ -857,9 +871,12 @@ int forward_staged(cotr_model* m, int B, int Q, cudaStream_t s) {
         if (m->shapes_seen.count(key) && m->graphs.size() < 256) {
             // second call with this shape: workspace, contexts and kernel attributes are in place -> capture
             cudaGraph_t graph = nullptr;
-            COTR_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            const int rc = forward_eager(m, w.img_stage, w.q_stage, B, Q, w.pred_stage, s);
-            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            // the legacy default stream (what torch hands over by default) cannot be captured: record on ours,
+            // the resulting graph is launched on the caller's stream either way
+            cudaStream_t cs = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) ? m->host_stream : s;
+            COTR_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            const int rc = forward_eager(m, w.img_stage, w.q_stage, B, Q, w.pred_stage, cs);
+            const cudaError_t e = cudaStreamEndCapture(cs, &graph);
             if (rc || e != cudaSuccess || graph == nullptr) {
                 if (graph) cudaGraphDestroy(graph);
                 if (!rc) set_error("cotr_forward: stream capture failed: %s", cudaGetErrorString(e));

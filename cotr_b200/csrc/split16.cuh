@@ -4,20 +4,24 @@
 
 namespace cotr {
 
-// x ~= hi + lo with ~22 mantissa bits.  Both terms saturate at the fp16 range, so the format represents |x| up to
-// 131008 and clamps beyond (never inf / NaN); below 2^-3 the lo term is an fp16 subnormal, i.e. the absolute error
-// floors at ~3e-8.
-__device__ __forceinline__ float sat16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+// x ~= hi + lo with ~22 mantissa bits.  Both terms saturate at the fp16 range (cvt.rn.satfinite -> one
+// F2FP.SATFINITE instruction), so the format represents |x| up to 131008 and clamps beyond (never inf / NaN); below
+// 2^-3 the lo term is an fp16 subnormal, i.e. the absolute error floors at ~3e-8.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {      // lo_elem -> bits [0,16)
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(sat16(a), sat16(b));
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(sat16(a - hf.x), sat16(b - hf.y));
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+    hi = pack_f16x2_sat(a, b);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = pack_f16x2_sat(a - hf.x, b - hf.y);
 }
 __device__ __forceinline__ void split_f16(float a, __half& hi, __half& lo) {
-    hi = __float2half_rn(sat16(a));
-    lo = __float2half_rn(sat16(a - __half2float(hi)));
+    const uint32_t h = pack_f16x2_sat(a, 0.f);
+    hi = __ushort_as_half((unsigned short)(h & 0xFFFFu));
+    const uint32_t l = pack_f16x2_sat(a - __half2float(hi), 0.f);
+    lo = __ushort_as_half((unsigned short)(l & 0xFFFFu));
 }
 __device__ __forceinline__ float2 join_f16x2(uint32_t hi, uint32_t lo) {
     const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));

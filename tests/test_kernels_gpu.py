@@ -74,10 +74,10 @@ def test_gemm_wide_dynamic_range(capi, path):
     """Operands spanning 1e-4 .. 3e2 (post-ReLU features are like that): the fp16 split must not lose the small ones."""
     g = _gen(5)
     M, N, K = 256, 128, 512
-    A = (torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, K, generator=g) * 3)).clamp(-3e2, 3e2).cuda()
+    A = (torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, K, generator=g) * 3)).clamp(-3e2, 3e2).cuda() * 0.5
     W = torch.randn(N, K, generator=g) * torch.exp(torch.randn(N, K, generator=g) * 2) * 1e-2
     ref = A.double() @ W.cuda().double().t()
-    assert ref.abs().max() < 1.2e5        # inside the split16 range (|x| <= 131008)
+    assert ref.abs().max() < 6.5e4        # full-precision range of split16 (hi alone saturates at 65504)
     out = capi.test_gemm(path, A, W.numpy())
     assert _rel(out, ref) < REL[path]
 

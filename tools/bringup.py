@@ -128,7 +128,41 @@ def gemm_timeline():
                   " ".join(f"{r[3 + 2 * i]}/{r[4 + 2 * i]}" for i in range(min(8, (K + 63) // 64))) +
                   f" | mma sawA/issued " + " ".join(f"{r[24 + 2 * i]}/{r[25 + 2 * i]}" for i in range(min(8, (K + 63) // 64))) +
                   f" | tma " + " ".join(str(r[44 + i]) for i in range(min(8, (K + 63) // 64))) +
-                  f" | final commit {r[41]} acc ready {r[20]} epi done {r[21]} end {r[60]}", flush=True)
+                  f" | final commit {r[41]} acc ready {r[20]} | epi chunk0 acc/apply/emit {r[30]}/{r[31]}/{r[32]} chunk1 {r[34]}/{r[35]}/{r[36]} before drain {r[38]}"
+                  f" epi done {r[21]} end {r[60]}", flush=True)
+
+
+def launch_profile():
+    """Per-launch CUDA-event durations of one eager forward (B=1, Q=1024), library profiler."""
+    import torch
+    from cotr_b200.models import build_model
+    from oracle import fixtures
+    sd = fixtures.make_state_dict(0)
+    model = build_model(None)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.cuda().eval()
+    img, q = fixtures.make_inputs(1, 1, 1024)
+    img = torch.from_numpy(img).cuda(); q = torch.from_numpy(q).cuda()
+    nat = model.native()
+    for _ in range(3):
+        model(img, q)
+    import collections
+    acc = collections.OrderedDict()
+    reps = 5
+    for _ in range(reps):
+        nat.profile_begin(1024)
+        model(img, q)
+        for i, (name, M, N, K, ms) in enumerate(nat.profile_end()):
+            key = (i, name, M, N, K)
+            acc[key] = acc.get(key, 0.0) + ms
+    total = 0.0
+    by_kind = collections.defaultdict(float)
+    for (i, name, M, N, K), ms in acc.items():
+        us = ms / reps * 1e3
+        total += us
+        by_kind[name] += us
+        print(f"  {i:3d} {name:14s} M={M:6d} N={N:5d} K={K:5d}  {us:7.1f} us", flush=True)
+    print(f"  total {total:.0f} us; by kind: " + ", ".join(f"{k} {v:.0f}" for k, v in by_kind.items()), flush=True)
 
 
 def attn_cases(path):
@@ -222,6 +256,8 @@ def run_stage(name):
         model_case(0)
     elif name == "timing":
         timing()
+    elif name == "launch_profile":
+        launch_profile()
     elif name == "gemm_timeline":
         gemm_timeline()
     elif name == "tc_precision":
