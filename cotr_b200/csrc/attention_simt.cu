@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(kWarps * 32) attention_simt_kernel(const AttnP
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
+    pdl_wait();
+    if (tid == 0) pdl_launch_dependents();
     for (int idx = tid; idx < kTokens * (kHeadDim / 8); idx += blockDim.x) {        // K rows: 8 elements per step
         const int key = idx >> 2, d8 = (idx & 3) * 8;
         float v[8];
@@ -104,8 +106,7 @@ int launch_attention_simt(const AttnParams& p, cudaStream_t s) {
     }
     COTR_CHECK(p.npairs <= 65535, "attention: too many pairs in one launch (%d)", p.npairs);
     dim3 grid((p.nq + kRowsPerCta - 1) / kRowsPerCta, kHeads, p.npairs);
-    attention_simt_kernel<<<grid, kWarps * 32, kSmemBytes, s>>>(p);
-    COTR_CHECK_CUDA(cudaGetLastError());
+    COTR_CHECK_CUDA(launch_kernel(attention_simt_kernel, grid, dim3(kWarps * 32), kSmemBytes, s, p));
     return 0;
 }
 

@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         const bool row_ok = qi < p.nq;
         const size_t grow = (size_t)pair_local * p.nq + (row_ok ? qi : 0);
         const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
+        pdl_wait();                                      // prologue above overlaps the previous kernel
+        if (t == 0) pdl_launch_dependents();
 
         // ---- stage Q (one row per thread) and K (4 keys per thread): 16-byte async copies ---------------------
         {
@@ -277,8 +279,7 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
     COTR_CHECK((p.ldq & 7) == 0 && (p.ldk & 7) == 0 && (p.ldo & 7) == 0 && (p.vt_pair_stride & 7) == 0,
                "attention_tc: leading dimensions must be multiples of 8 elements");
     dim3 grid((p.nq + kTile - 1) / kTile, kHeads, p.npairs);
-    attention_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
-    COTR_CHECK_CUDA(cudaGetLastError());
+    COTR_CHECK_CUDA(launch_kernel(attention_tc_kernel, grid, dim3(kThreads), kSmemBytes, s, p));
     return 0;
 }
 

@@ -27,6 +27,61 @@ void set_error(const char* fmt, ...);
         }                                                                                          \
     } while (0)
 
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the forward is launched with the programmatic-stream-serialization
+// attribute: it may start (barrier init, TMEM allocation, weight prefetch by TMA) while its predecessor in the
+// stream / graph is still draining, and calls pdl_wait() before it first touches memory the predecessor produces
+// (or still reads).  At batch 1 the forward is ~135 latency-bound launches, so hiding launch + prologue matters.
+// ---------------------------------------------------------------------------------------------------------------
+extern int g_use_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Same, with a thread-block cluster of (1, 1, cluster_z) CTAs (grid.z must equal cluster_z).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         int cluster_z, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (g_use_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_z > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = 1;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = (unsigned)cluster_z;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 constexpr int kDModel = 256;
 constexpr int kHeads = 8;
 constexpr int kHeadDim = 32;

@@ -10,6 +10,8 @@ namespace {
 __global__ void maxpool_3x3s2_nhwc_kernel(const CSplit16 in, const Split16 out, int N, int H, int W, int C8) {
     const int OH = H / 2, OW = W / 2;
     const size_t total = (size_t)N * OH * OW * C8;
+    pdl_wait();
+    if (threadIdx.x == 0) pdl_launch_dependents();
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         const int c8 = idx % C8;
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(256) layernorm256_kernel(const CSplit16 x, con
                                                            const Split16 out, int rows) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_wait();
+    if (threadIdx.x == 0) pdl_launch_dependents();
     if (warp >= rows) return;
     const size_t off = (size_t)warp * kDModel + lane * 8;
     float v[8];
@@ -82,6 +86,8 @@ __global__ void __launch_bounds__(256) layernorm256_kernel(const CSplit16 x, con
 // channel 2(k-1)+a = sin(fp32(k*pi) * p_a), channel 128 + 2(k-1)+a = cos(...).  Accurate sincosf: |angle| <= 64*pi.
 __global__ void __launch_bounds__(128) query_encode_kernel(const float* __restrict__ queries, const Split16 qpos, int rows) {
     const int row = blockIdx.x;
+    pdl_wait();
+    if (threadIdx.x == 0) pdl_launch_dependents();
     if (row >= rows) return;
     const int t = threadIdx.x;          // 0..127 = 2*(k-1) + axis
     const int k = (t >> 1) + 1;
@@ -122,29 +128,25 @@ int grid_for(size_t total, int block) {
 int launch_maxpool_3x3s2_nhwc(CSplit16 in, Split16 out, int N, int H, int W, int C, cudaStream_t s) {
     COTR_CHECK((C & 7) == 0 && (H & 1) == 0 && (W & 1) == 0, "maxpool: unsupported shape");
     const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
-    maxpool_3x3s2_nhwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, N, H, W, C / 8);
-    COTR_CHECK_CUDA(cudaGetLastError());
+    COTR_CHECK_CUDA(launch_kernel(maxpool_3x3s2_nhwc_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, in, out, N, H, W, C / 8));
     return 0;
 }
 
 int launch_layernorm(CSplit16 x, const float* gamma, const float* beta, Split16 out, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
-    layernorm256_kernel<false><<<(rows + 7) / 8, 256, 0, s>>>(x, nullptr, gamma, beta, out, rows);
-    COTR_CHECK_CUDA(cudaGetLastError());
+    COTR_CHECK_CUDA(launch_kernel(layernorm256_kernel<false>, dim3((rows + 7) / 8), dim3(256), 0, s, x, (const float*)nullptr, gamma, beta, out, rows));
     return 0;
 }
 
 int launch_layernorm_f32(const float* x, const float* gamma, const float* beta, Split16 out, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
-    layernorm256_kernel<true><<<(rows + 7) / 8, 256, 0, s>>>(CSplit16{nullptr, nullptr}, x, gamma, beta, out, rows);
-    COTR_CHECK_CUDA(cudaGetLastError());
+    COTR_CHECK_CUDA(launch_kernel(layernorm256_kernel<true>, dim3((rows + 7) / 8), dim3(256), 0, s, CSplit16{nullptr, nullptr}, x, gamma, beta, out, rows));
     return 0;
 }
 
 int launch_query_encode(const float* queries, Split16 qpos, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
-    query_encode_kernel<<<rows, 128, 0, s>>>(queries, qpos, rows);
-    COTR_CHECK_CUDA(cudaGetLastError());
+    COTR_CHECK_CUDA(launch_kernel(query_encode_kernel, dim3(rows), dim3(128), 0, s, queries, qpos, rows));
     return 0;
 }
 

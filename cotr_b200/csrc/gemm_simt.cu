@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p, floa
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
+    pdl_wait();
+    if (tid == 0) pdl_launch_dependents();
 
     const int lrow = tid >> 2;          // 0..63
     const int lk = (tid & 3) * 4;       // 0,4,8,12
@@ -116,8 +118,7 @@ int launch_gemm_simt_raw(const GemmParams& p, float* raw_out, cudaStream_t s) {
     COTR_CHECK(p.a_mode != A_CONV_NHWC || (p.C & 7) == 0, "gemm_simt: NHWC conv needs C %% 8 == 0 (C=%d)", p.C);
     COTR_CHECK(p.ln_gamma == nullptr, "gemm_simt: fused LayerNorm is a tensor-core-path feature");
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-    gemm_simt_kernel<<<grid, 256, 0, s>>>(p, raw_out);
-    COTR_CHECK_CUDA(cudaGetLastError());
+    COTR_CHECK_CUDA(launch_kernel(gemm_simt_kernel, grid, dim3(256), 0, s, p, raw_out));
     return 0;
 }
 

@@ -35,6 +35,7 @@
 namespace cotr {
 
 int g_tc_variant = 0;                   // bring-up switch (reserved)
+int g_use_pdl = 1;                      // programmatic dependent launch (common.cuh); cotr_debug_set_variant bit 8 clears it
 long long* g_tc_timestamps = nullptr;   // debug: 64 clock64() stamps per CTA (cotr_debug_set_timestamps), else null
 
 namespace {
@@ -103,7 +104,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
-    const int KC = (p.K + BK - 1) / BK;
+    // split-K: gridDim.z CTAs of one cluster (cluster dims 1 x 1 x gridDim.z) share the output tile; CTA z walks the
+    // K chunks [it0, it0 + KC) and CTAs z > 0 hand their partial sums to CTA 0 through distributed shared memory.
+    const int ksplit = gridDim.z;
+    const int kz = blockIdx.z;
+    const int KC = ((p.K + BK - 1) / BK) / ksplit;
+    const int it0 = kz * KC;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
@@ -131,6 +137,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         for (int i = 0; i < 8; ++i) rows[i] = decode_a_row(p, m0 + rb + 16 * i);
         const uint32_t a_off = (uint32_t)rb * 128u + (uint32_t)((kg ^ (rb & 7)) << 4);   // swizzled chunk position
         const uint32_t dst0 = smem_u32(stage_base) + a_off;
+        // everything above (and the weight TMA of warp 4) overlaps the previous kernel; activations do not
+        pdl_wait();
+        if (threadIdx.x == 0) pdl_launch_dependents();
         if (threadIdx.x == 0) COTR_TS(2);
 
 #pragma unroll 1
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
             mbar_wait(&empty[s], ph ^ 1u);
             if (threadIdx.x == 0 && it < 8) COTR_TS(3 + 2 * it);
-            const int k0 = it * BK;
+            const int k0 = (it0 + it) * BK;
             if constexpr (MODE != LD_STEM) {
                 const uint32_t dst = dst0 + (uint32_t)s * C::kStage;
                 int kh = 0, kw = 0, koff = k0 + kg * 8;          // LD_GATHER: koff = column inside the row
@@ -241,6 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         };
         // v[0..15] = acc_scale * (sum over all accumulators of columns [c, c+16)); all TMEM loads of the chunk are
         // issued back to back and waited for once.
+        constexpr uint32_t kPartPitch = BN * 4u + 16u;            // fp32 partial tile rows, padded
+        constexpr uint32_t kPartBytes = 128u * kPartPitch;
+        constexpr uint32_t kPartOffset = 4u * C::kWarpStaging;    // behind the output staging area
         auto load_acc = [&](int c, float (&v)[16]) {
             uint32_t r[C::kSlots][16];
             __syncwarp();
@@ -255,8 +267,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 float y = __uint_as_float(r[0][j]);
 #pragma unroll
                 for (int a = 1; a < C::kMain; ++a) y += __uint_as_float(r[a][j]);
-                v[j] = (x + y) * acc_scale;
+                v[j] = x + y;
             }
+            if (ksplit > 1 && kz == 0) {                  // leader: add the partial sums the peers pushed over DSMEM
+                const uint8_t* part = stage_base + kPartOffset + (uint32_t)(warp * 32 + lane) * kPartPitch + c * 4;
+                for (int peer = 0; peer < ksplit - 1; ++peer) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(part + (uint32_t)peer * kPartBytes + j * 4);
+                        v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= acc_scale;
         };
 
         // Output path.  split16 row-major tiles are staged in shared memory (the pipeline stages are idle once the
@@ -318,6 +342,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         mbar_wait(accum_full, 0);
         tcgen05_fence_after();
         if (threadIdx.x == 0) COTR_TS(20);
+        if (ksplit > 1) {
+            // barrier 1: every CTA's MMAs have retired, so the leader's pipeline stages are free to receive partials
+            cluster_arrive();
+            cluster_wait();
+            if (kz != 0) {
+                const uint32_t local = smem_u32(stage_base) + kPartOffset + (uint32_t)(kz - 1) * kPartBytes +
+                                       (uint32_t)(warp * 32 + lane) * kPartPitch;
+                const uint32_t remote = map_to_cta(local, 0);
+                const float keep = acc_scale;                       // load_acc scales; undo so the leader scales once
+                (void)keep;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 16) {
+                    uint32_t r[C::kSlots][16];
+                    __syncwarp();
+#pragma unroll
+                    for (int a = 0; a < C::kSlots; ++a) tmem_ld16_issue(trow + a * BN + c, r[a]);
+#pragma unroll
+                    for (int a = 0; a < C::kSlots; ++a) tmem_ld16_fence(r[a]);
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x = __uint_as_float(r[C::kMain][j]);
+                        if (C::kCorr == 2) x += __uint_as_float(r[C::kMain + 1][j]);
+                        float y = __uint_as_float(r[0][j]);
+#pragma unroll
+                        for (int a = 1; a < C::kMain; ++a) y += __uint_as_float(r[a][j]);
+                        v[j] = x + y;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) st_cluster_f32x4(remote + c * 4 + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+            // barrier 2: partials are visible in the leader's shared memory; the peers are done
+            cluster_arrive();
+            cluster_wait();
+        }
+        if (ksplit == 1 || kz == 0) {
 
         if constexpr (!LN) {
 #pragma unroll
@@ -396,6 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             }
             drain();
         }
+        }   // leader / unsplit epilogue
         if (threadIdx.x == 0) COTR_TS(21);
     } else if (warp == 4) {
         // ================= weight producer: bulk TMA of the pre-swizzled fp16 hi/lo image ========================
@@ -409,13 +471,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 mbar_arrive_expect_tx(&full_b[s], 2u * C::kBPlane);
                 uint8_t* b_dst = stage_base + (size_t)s * C::kStage + 2 * kAPlane;
                 // image: [k chunk][plane][npad rows][128 bytes]; the BN rows of this tile are contiguous per plane
-                const uint8_t* src = wimg + (((size_t)it * 2) * npad + n0) * 128;
+                const uint8_t* src = wimg + (((size_t)(it0 + it) * 2) * npad + n0) * 128;
                 tma_bulk_g2s(b_dst, src, C::kBPlane, &full_b[s]);
                 tma_bulk_g2s(b_dst + C::kBPlane, src + (size_t)npad * 128, C::kBPlane, &full_b[s]);
                 if (it < 8) COTR_TS(44 + it);
             }
         }
         __syncwarp();
+        if (ksplit > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
     } else {
         // ================= MMA issuer ===========================================================================
         if (lane == 0) {
@@ -454,6 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             COTR_TS(41);
         }
         __syncwarp();
+        if (ksplit > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
     }
 
     tcgen05_fence_before();
@@ -473,8 +537,19 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     }
     const int npad = tc_npad(p.N);
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-    gemm_tc_kernel<BN, LN, MODE><<<grid, kThreads, C::kSmemBytes, s>>>(p, npad, g_tc_timestamps);
-    COTR_CHECK_CUDA(cudaGetLastError());
+    // Split-K over a thread-block cluster for long reductions on under-filled grids (the K loop is the serial part of
+    // these latency-bound launches): 4 or 2 CTAs per output tile, each >= 4 chunks, at most ~one wave of CTAs.
+    int ksplit = 1;
+    if constexpr (!LN && BN <= 64 && MODE != LD_STEM) {
+        const int kc = (p.K + BK - 1) / BK;
+        const long long ctas = (long long)grid.x * grid.y;
+        if (!(g_tc_variant & 512) && kc >= 16) {
+            if (kc % 4 == 0 && ctas * 4 <= 160) ksplit = 4;
+            else if (kc % 2 == 0 && ctas * 2 <= 160) ksplit = 2;
+        }
+    }
+    grid.z = ksplit;
+    COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), C::kSmemBytes, s, ksplit, p, npad, g_tc_timestamps));
     return 0;
 }
 

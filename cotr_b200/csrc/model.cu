@@ -1013,7 +1013,7 @@ int cotr_set_gemm_path(cotr_model* m, int path) {
     return 0;
 }
 
-void cotr_debug_set_variant(int variant) { g_tc_variant = variant; }
+void cotr_debug_set_variant(int variant) { g_tc_variant = variant; g_use_pdl = (variant & 256) ? 0 : 1; }
 void cotr_debug_set_timestamps(void* dev_buffer) { g_tc_timestamps = reinterpret_cast<long long*>(dev_buffer); }
 
 // ---- kernel-level test hooks: fp32 device tensors in / out, converted to split16 around the kernel under test -------

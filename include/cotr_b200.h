@@ -132,7 +132,7 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
 /* out[(p*nq+i), h*32+d] = softmax(q k^T) v per head; q (npairs*nq,256), k/v (npairs*512,256), all DEVICE, ld 256. */
 int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const float* v_dev, float* out_dev,
                         int nq, int npairs);
-/* reserved bring-up switch. */
+/* bring-up switch: bit 8 (256) disables programmatic dependent launch. */
 void cotr_debug_set_variant(int variant);
 /* debug timeline of the tcgen05 GEMM: DEVICE buffer of 64 int64 per CTA receiving clock64() deltas of the pipeline
  * events of every following GEMM launch (NULL switches it off).  Slot layout: tools/bringup.py::gemm_timeline. */
