@@ -42,6 +42,8 @@ _PROTOTYPES = {
     "cotr_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "cotr_preprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_set_graph_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cotr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "cotr_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -164,6 +166,16 @@ class NativeModel:
         check(lib().cotr_forward_host(self.handle, ctypes.c_void_p(img_np.ctypes.data), ctypes.c_void_p(queries_np.ctypes.data),
                                       B, Q, ctypes.c_void_p(out_np.ctypes.data)), "cotr_forward_host")
         return out_np
+
+    def preprocess(self, img_from_dev, img_to_dev, rects):
+        """uint8 HWC device images + (n,6) int32 crop rectangles -> (n,3,256,512) fp32 normalised canvases (device)."""
+        rects = np.ascontiguousarray(rects, dtype=np.int32)
+        n = rects.shape[0]
+        canvas = torch.empty((n, 3, 256, 512), dtype=torch.float32, device=img_from_dev.device)
+        check(lib().cotr_preprocess(self.handle, _ptr(img_from_dev), img_from_dev.shape[0], img_from_dev.shape[1],
+                                    _ptr(img_to_dev), img_to_dev.shape[0], img_to_dev.shape[1],
+                                    ctypes.c_void_p(rects.ctypes.data), n, _ptr(canvas), self._stream()), "cotr_preprocess")
+        return canvas
 
     def set_graph_mode(self, enabled):
         check(lib().cotr_set_graph_mode(self.handle, int(bool(enabled))), "cotr_set_graph_mode")

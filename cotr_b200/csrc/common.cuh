@@ -179,6 +179,13 @@ int launch_query_encode(const float* queries, Split16 qpos, int rows, cudaStream
 int launch_f32_to_split16(const float* in, Split16 out, size_t n, cudaStream_t s);
 int launch_split16_to_f32(CSplit16 in, float* out, size_t n, cudaStream_t s);
 
+// Device-side crop + Pillow-exact resize + normalise (preprocess.cu)
+struct Preprocessor;
+Preprocessor* preprocessor_create();
+void preprocessor_destroy(Preprocessor* p);
+int preprocess_launch(Preprocessor* p, const unsigned char* img_from, int hf, int wf, const unsigned char* img_to, int ht, int wt,
+                      const int* rects_host, int n, float* canvas_dev, cudaStream_t s);
+
 // Bytes of the pre-tiled fp16 hi/lo image of an [N,K] weight matrix, and the host-side packer (returns acc_scale).
 size_t tc_weight_bytes(int N, int K);
 float tc_pack_weight(const float* w, int N, int K, void* dst_host);

@@ -44,7 +44,7 @@ using namespace tc;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;
 constexpr uint32_t kAPlane = BM * 128;         // one fp16 plane (hi or lo) of the 128 x 64 A tile: 128 rows x 128 bytes
 
 enum LoaderMode : int { LD_GATHER = 0, LD_CONV = 1, LD_STEM = 2 };
@@ -69,7 +69,11 @@ struct Cfg {
     static constexpr uint32_t kOutPitch = BN * 2u + 16u;
     static constexpr uint32_t kWarpStaging = 2u * 32u * kOutPitch;
     static constexpr int kChunksN = BN / 16;
-    static constexpr int kRing = kChunksN < 4 ? kChunksN : 4;          // epilogue operand prefetch depth
+    // Epilogue warps: the four TMEM lane quarters x kEpiHalves column halves (warp w reads lanes 32 (w % 4) ...,
+    // columns [w / 4 * BN / 2, ...)).  The LayerNorm tile (BN = 256) keeps one thread per full row.
+    static constexpr int kEpiHalves = (BN >= 32 && BN < 256) ? 2 : 1;
+    static constexpr int kChunksW = kChunksN / kEpiHalves;             // 16-column chunks per epilogue warp
+    static constexpr int kRing = kChunksW < 4 ? kChunksW : 4;          // epilogue operand prefetch depth
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
     static constexpr uint32_t kSmemBytes = kStages * kStage + 2048;     // + alignment slack + barriers
     static_assert(kStages >= 2, "pipeline needs at least two stages");
@@ -177,28 +181,119 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             } else {
                 uint8_t* a_hi = stage_base + (size_t)s * C::kStage + a_off;
                 uint8_t* a_lo = a_hi + kAPlane;
-#pragma unroll 1
-                for (int i = 0; i < 8; ++i) {
-                    const float4 v0 = load_stem4(p, rows[i], k0 + kg * 8);
-                    const float4 v1 = load_stem4(p, rows[i], k0 + kg * 8 + 4);
-                    uint4 hi, lo;
-                    split_f16x2(v0.x, v0.y, hi.x, lo.x);
-                    split_f16x2(v0.z, v0.w, hi.y, lo.y);
-                    split_f16x2(v1.x, v1.y, hi.z, lo.z);
-                    split_f16x2(v1.z, v1.w, hi.w, lo.w);
-                    *reinterpret_cast<uint4*>(a_hi + i * 2048) = hi;
-                    *reinterpret_cast<uint4*>(a_lo + i * 2048) = lo;
+                // the 8 patch elements this thread fetches are the same for its 8 rows: decode them once per chunk
+                int rel[8], dh[8], dw[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int kk = k0 + kg * 8 + t;
+                    const int tap = kk / 3, c = kk - tap * 3;
+                    const int kh = tap / 7, kw = tap - kh * 7;
+                    dh[t] = kk < p.K ? kh : -100000;             // beyond K: never in bounds -> zero
+                    dw[t] = kw;
+                    rel[t] = c * 256 * 512 + kh * 512 + kw;
+                }
+                // 4 rows x 8 scalar gathers in flight per pass (the loads are L2 hits of ~700 cycles: issue, then convert)
+#pragma unroll
+                for (int i0 = 0; i0 < 8; i0 += 4) {
+                    float e[4][8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const ARow& r = rows[i0 + i];
+                        const float* base = p.a_f32 + r.off + (ptrdiff_t)r.ih0 * 512 + r.iw0;
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const int ih = r.ih0 + dh[t], iw = r.iw0 + dw[t];
+                            const bool ok = r.valid && ih >= 0 && ih < 256 && iw >= 0 && iw < 256;
+                            e[i][t] = ok ? __ldg(base + rel[t]) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 hi, lo;
+                        split_f16x2(e[i][0], e[i][1], hi.x, lo.x);
+                        split_f16x2(e[i][2], e[i][3], hi.y, lo.y);
+                        split_f16x2(e[i][4], e[i][5], hi.z, lo.z);
+                        split_f16x2(e[i][6], e[i][7], hi.w, lo.w);
+                        *reinterpret_cast<uint4*>(a_hi + (i0 + i) * 2048) = hi;
+                        *reinterpret_cast<uint4*>(a_lo + (i0 + i) * 2048) = lo;
+                    }
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&full_a[s]);
             }
             if (threadIdx.x == 0 && it < 8) COTR_TS(4 + 2 * it);
         }
+    } else if (warp == 4) {
+        // ================= weight producer: bulk TMA of the pre-swizzled fp16 hi/lo image ========================
+        if (lane == 0) {
+            const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.Wtc);
+#pragma unroll 1
+            for (int it = 0; it < KC; ++it) {
+                const int s = it % C::kStages;
+                const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_b[s], 2u * C::kBPlane);
+                uint8_t* b_dst = stage_base + (size_t)s * C::kStage + 2 * kAPlane;
+                // image: [k chunk][plane][npad rows][128 bytes]; the BN rows of this tile are contiguous per plane
+                const uint8_t* src = wimg + (((size_t)(it0 + it) * 2) * npad + n0) * 128;
+                tma_bulk_g2s(b_dst, src, C::kBPlane, &full_b[s]);
+                tma_bulk_g2s(b_dst + C::kBPlane, src + (size_t)npad * 128, C::kBPlane, &full_b[s]);
+                if (it < 8) COTR_TS(44 + it);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ================= MMA issuer ===========================================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
+            const uint32_t hi_word = desc_hi_sw128();
+            const uint32_t corr_a = tmem_base + (uint32_t)C::kMain * BN;
+            const uint32_t corr_b = tmem_base + (uint32_t)(C::kMain + C::kCorr - 1) * BN;
+#pragma unroll 1
+            for (int it = 0; it < KC; ++it) {
+                const int s = it % C::kStages;
+                const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
+                mbar_wait(&full_a[s], ph);
+                if (it < 8) COTR_TS(24 + 2 * it);
+                mbar_wait(&full_b[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(stage_base + (size_t)s * C::kStage);
+                const uint32_t a_h0 = desc_lo_sw128(a_addr);
+                const uint32_t b_h0 = desc_lo_sw128(a_addr + 2 * kAPlane);
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ++ks) {
+                    const int g = it * (BK / 16) + ks;                       // global K step
+                    // a K step of 16 halves = 32 bytes inside the 128-byte swizzle atom: +2 in the address field
+                    const uint64_t dah = make_desc(a_h0 + 2 * ks, hi_word);
+                    const uint64_t dal = make_desc(a_h0 + (kAPlane >> 4) + 2 * ks, hi_word);
+                    const uint64_t dbh = make_desc(b_h0 + 2 * ks, hi_word);
+                    const uint64_t dbl = make_desc(b_h0 + (C::kBPlane >> 4) + 2 * ks, hi_word);
+                    const uint32_t main_col = tmem_base + (uint32_t)(g % C::kMain) * BN;
+                    umma_f16_ss(corr_a, dal, dbh, idesc, g != 0);
+                    umma_f16_ss(main_col, dah, dbh, idesc, g >= C::kMain);
+                    umma_f16_ss(corr_b, dah, dbl, idesc, C::kCorr == 1 ? true : g != 0);
+                }
+                umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
+                if (it < 8) COTR_TS(25 + 2 * it);
+            }
+            umma_commit(accum_full);
+            COTR_TS(41);
+        }
+        __syncwarp();
+    }
 
-        // ================= epilogue: TMEM -> registers -> global =============================================
-        const int row = m0 + warp * 32 + lane;
+    // ================= epilogue: TMEM -> registers -> global ======================================================
+    // Warps 0-3 arrive here when their last copies are issued, warps 4/5 when the last TMA / MMA is issued, 6/7 at once.
+    const int ew = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = warp >> 2;              // column half of the tile it handles
+    if (half >= C::kEpiHalves) {
+        if (ksplit > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
+    } else {
+        if (warp >= 4) pdl_wait();           // residual / add operands come from the previous kernels
+        const int cbeg = half * C::kChunksW * 16;
+        const int row = m0 + ew * 32 + lane;
         const bool row_ok = row < p.M;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
         const float* add_row = (row_ok && p.addmat) ? p.addmat + (size_t)(row % p.add_period) * p.ld_add : nullptr;
         const bool has_res = row_ok && p.res.hi != nullptr;
         const size_t res_off = (size_t)(row_ok ? row : 0) * p.ldr;
@@ -270,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 v[j] = x + y;
             }
             if (ksplit > 1 && kz == 0) {                  // leader: add the partial sums the peers pushed over DSMEM
-                const uint8_t* part = stage_base + kPartOffset + (uint32_t)(warp * 32 + lane) * kPartPitch + c * 4;
+                const uint8_t* part = stage_base + kPartOffset + (uint32_t)(ew * 32 + lane) * kPartPitch + c * 4;
                 for (int peer = 0; peer < ksplit - 1; ++peer) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -284,12 +379,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         };
 
         // Output path.  split16 row-major tiles are staged in shared memory (the pipeline stages are idle once the
-        // accumulator is complete; each warp stages and drains only its own 32 rows, so a __syncwarp suffices) and
-        // written out as full 128-byte-coalesced rows; a thread-per-row direct store would touch 32 different cache
-        // lines per instruction.  Transposed value blocks and the fp32 prediction head keep the direct path.
+        // accumulator is complete) and written out as full coalesced rows; a thread-per-row direct store would touch
+        // 32 different cache lines per instruction.  The two warps of a lane quarter stage their column halves into the
+        // same 32-row region, meet on a named barrier and drain one fp16 plane each.  Transposed value blocks and the
+        // fp32 prediction head keep the direct path.
         size_t tile_base = 0;
         const bool direct = p.out_f32 != nullptr || out_location(p, m0, n0, tile_base);
-        uint8_t* stg = stage_base + (uint32_t)warp * C::kWarpStaging + (uint32_t)lane * C::kOutPitch;
+        uint8_t* stg = stage_base + (uint32_t)ew * C::kWarpStaging + (uint32_t)lane * C::kOutPitch;
         auto emit16 = [&](int c, const float (&v)[16]) {          // c = column inside the tile
             if (direct) {
                 if (row_ok && n0 + c < p.N) store16(p, row, n0 + c, v);
@@ -306,37 +402,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             *reinterpret_cast<uint4*>(d + 32 * C::kOutPitch) = l0;
             *reinterpret_cast<uint4*>(d + 32 * C::kOutPitch + 16) = l1;
         };
-        auto drain = [&]() {
-            if (direct) return;
-            __syncwarp();
+        auto drain_plane = [&](int plane) {
             constexpr int kLanesPerRow = BN * 2 / 16;                     // 16-byte pieces per row of one plane
             constexpr int kRowsPerPass = kLanesPerRow >= 32 ? 1 : 32 / kLanesPerRow;
             constexpr int kPiecesPerLane = kLanesPerRow > 32 ? kLanesPerRow / 32 : 1;
-            const uint8_t* wbase = stage_base + (uint32_t)warp * C::kWarpStaging;
+            const uint8_t* wbase = stage_base + (uint32_t)ew * C::kWarpStaging;
             const int r_in = kLanesPerRow >= 32 ? 0 : lane / kLanesPerRow;
             const int piece0 = kLanesPerRow >= 32 ? lane : lane % kLanesPerRow;
-#pragma unroll
-            for (int plane = 0; plane < 2; ++plane) {
-                __half* gout = (plane == 0 ? p.out.hi : p.out.lo) + tile_base;     // element (m0, n0 mapped)
+            __half* gout = (plane == 0 ? p.out.hi : p.out.lo) + tile_base;     // element (m0, n0 mapped)
 #pragma unroll 4
-                for (int r0 = 0; r0 < 32; r0 += kRowsPerPass) {
-                    const int rr = r0 + r_in;
-                    const int grow_ = m0 + warp * 32 + rr;
+            for (int r0 = 0; r0 < 32; r0 += kRowsPerPass) {
+                const int rr = r0 + r_in;
+                const int grow_ = m0 + ew * 32 + rr;
 #pragma unroll
-                    for (int q = 0; q < kPiecesPerLane; ++q) {
-                        const int piece = piece0 + q * 32;
-                        const uint4 val = *reinterpret_cast<const uint4*>(wbase + (uint32_t)(plane * 32 + rr) * C::kOutPitch + piece * 16);
-                        if (grow_ < p.M)
-                            *reinterpret_cast<uint4*>(gout + (size_t)(warp * 32 + rr) * p.ldc + piece * 8) = val;
-                    }
+                for (int q = 0; q < kPiecesPerLane; ++q) {
+                    const int piece = piece0 + q * 32;
+                    const uint4 val = *reinterpret_cast<const uint4*>(wbase + (uint32_t)(plane * 32 + rr) * C::kOutPitch + piece * 16);
+                    if (grow_ < p.M)
+                        *reinterpret_cast<uint4*>(gout + (size_t)(ew * 32 + rr) * p.ldc + piece * 8) = val;
                 }
+            }
+        };
+        auto drain = [&]() {
+            if (direct) return;
+            if constexpr (C::kEpiHalves == 2) {
+                named_barrier_sync(1 + ew, 64);                           // both column halves of these 32 rows are staged
+                drain_plane(half);
+            } else {
+                __syncwarp();
+                drain_plane(0);
+                drain_plane(1);
             }
         };
 
         // The loader warps finish issuing their copies several pipeline stages before the last MMA retires: use that
         // slack to get the epilogue's global operands in flight (kRing chunks deep), then keep the ring full.
         EpiOperands ops[C::kRing];
-        const int nbase = LN ? 0 : n0;
+        const int nbase = (LN ? 0 : n0) + cbeg;
 #pragma unroll
         for (int i = 0; i < C::kRing; ++i) prefetch(nbase + 16 * i, ops[i]);
         mbar_wait(accum_full, 0);
@@ -348,12 +450,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             cluster_wait();
             if (kz != 0) {
                 const uint32_t local = smem_u32(stage_base) + kPartOffset + (uint32_t)(kz - 1) * kPartBytes +
-                                       (uint32_t)(warp * 32 + lane) * kPartPitch;
+                                       (uint32_t)(ew * 32 + lane) * kPartPitch;
                 const uint32_t remote = map_to_cta(local, 0);
-                const float keep = acc_scale;                       // load_acc scales; undo so the leader scales once
-                (void)keep;
+                // unscaled partial sums travel; the leader applies acc_scale once in load_acc
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 16) {
+                for (int ci = 0; ci < C::kChunksW; ++ci) {
+                    const int c = cbeg + ci * 16;
                     uint32_t r[C::kSlots][16];
                     __syncwarp();
 #pragma unroll
@@ -382,8 +484,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 
         if constexpr (!LN) {
 #pragma unroll
-            for (int ci = 0; ci < C::kChunksN; ++ci) {
-                const int c = ci * 16;
+            for (int ci = 0; ci < C::kChunksW; ++ci) {
+                const int c = cbeg + ci * 16;
                 const int nb = n0 + c;
                 float v[16];
                 load_acc(c, v);
@@ -402,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 if (threadIdx.x == 0 && ci < 2) COTR_TS(31 + 4 * ci);
                 emit16(c, v);
                 if (threadIdx.x == 0 && ci < 2) COTR_TS(32 + 4 * ci);
-                if (ci + C::kRing < C::kChunksN) prefetch(nb + 16 * C::kRing, ops[ci % C::kRing]);
+                if (ci + C::kRing < C::kChunksW) prefetch(nb + 16 * C::kRing, ops[ci % C::kRing]);
             }
             if (threadIdx.x == 0) COTR_TS(38);
             drain();
@@ -459,65 +561,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         }
         }   // leader / unsplit epilogue
         if (threadIdx.x == 0) COTR_TS(21);
-    } else if (warp == 4) {
-        // ================= weight producer: bulk TMA of the pre-swizzled fp16 hi/lo image ========================
-        if (lane == 0) {
-            const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.Wtc);
-#pragma unroll 1
-            for (int it = 0; it < KC; ++it) {
-                const int s = it % C::kStages;
-                const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_b[s], 2u * C::kBPlane);
-                uint8_t* b_dst = stage_base + (size_t)s * C::kStage + 2 * kAPlane;
-                // image: [k chunk][plane][npad rows][128 bytes]; the BN rows of this tile are contiguous per plane
-                const uint8_t* src = wimg + (((size_t)(it0 + it) * 2) * npad + n0) * 128;
-                tma_bulk_g2s(b_dst, src, C::kBPlane, &full_b[s]);
-                tma_bulk_g2s(b_dst + C::kBPlane, src + (size_t)npad * 128, C::kBPlane, &full_b[s]);
-                if (it < 8) COTR_TS(44 + it);
-            }
-        }
-        __syncwarp();
-        if (ksplit > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
-    } else {
-        // ================= MMA issuer ===========================================================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
-            const uint32_t hi_word = desc_hi_sw128();
-            const uint32_t corr_a = tmem_base + (uint32_t)C::kMain * BN;
-            const uint32_t corr_b = tmem_base + (uint32_t)(C::kMain + C::kCorr - 1) * BN;
-#pragma unroll 1
-            for (int it = 0; it < KC; ++it) {
-                const int s = it % C::kStages;
-                const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-                mbar_wait(&full_a[s], ph);
-                if (it < 8) COTR_TS(24 + 2 * it);
-                mbar_wait(&full_b[s], ph);
-                tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(stage_base + (size_t)s * C::kStage);
-                const uint32_t a_h0 = desc_lo_sw128(a_addr);
-                const uint32_t b_h0 = desc_lo_sw128(a_addr + 2 * kAPlane);
-#pragma unroll
-                for (int ks = 0; ks < BK / 16; ++ks) {
-                    const int g = it * (BK / 16) + ks;                       // global K step
-                    // a K step of 16 halves = 32 bytes inside the 128-byte swizzle atom: +2 in the address field
-                    const uint64_t dah = make_desc(a_h0 + 2 * ks, hi_word);
-                    const uint64_t dal = make_desc(a_h0 + (kAPlane >> 4) + 2 * ks, hi_word);
-                    const uint64_t dbh = make_desc(b_h0 + 2 * ks, hi_word);
-                    const uint64_t dbl = make_desc(b_h0 + (C::kBPlane >> 4) + 2 * ks, hi_word);
-                    const uint32_t main_col = tmem_base + (uint32_t)(g % C::kMain) * BN;
-                    umma_f16_ss(corr_a, dal, dbh, idesc, g != 0);
-                    umma_f16_ss(main_col, dah, dbh, idesc, g >= C::kMain);
-                    umma_f16_ss(corr_b, dah, dbl, idesc, C::kCorr == 1 ? true : g != 0);
-                }
-                umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
-                if (it < 8) COTR_TS(25 + 2 * it);
-            }
-            umma_commit(accum_full);
-            COTR_TS(41);
-        }
-        __syncwarp();
-        if (ksplit > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
     }
 
     tcgen05_fence_before();

@@ -123,6 +123,7 @@ struct cotr_model {
     std::map<long long, cudaGraphExec_t> graphs;
     std::map<long long, int> graph_launches;
     std::set<long long> shapes_seen;
+    cotr::Preprocessor* pre = nullptr;         // device-side crop / resize / normalise (cotr_preprocess)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_events;      // 2 per record
     std::vector<cotr_launch_record> prof_records;
@@ -392,10 +393,19 @@ int ws_alloc_f32(float** p, size_t elems) {
 }
 void ws_free_f32(float** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
 
+// Captured graphs embed workspace / staging / context addresses: whenever one of those is reallocated every graph is
+// stale.  The shapes stay "seen", so the next call of each shape re-captures against the new buffers.
+void drop_graphs(cotr_model* m) {
+    for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+    m->graphs.clear();
+    m->graph_launches.clear();
+}
+
 int ensure_encode_ws(cotr_model* m, int B) {
     Workspace& w = m->ws;
     if (B <= w.cap_pairs) return 0;
     COTR_CHECK_CUDA(cudaDeviceSynchronize());
+    drop_graphs(m);
     Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh};
     for (Split16* b : bufs) ws_free(b);
     ws_free_f32(&w.ln_tmp);
@@ -414,6 +424,7 @@ int ensure_decode_ws(cotr_model* m, int rows) {
     Workspace& w = m->ws;
     if (rows <= w.cap_rows) return 0;
     COTR_CHECK_CUDA(cudaDeviceSynchronize());
+    drop_graphs(m);
     Split16* bufs[] = {&w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2};
     for (Split16* b : bufs) ws_free(b);
     ws_free_f32(&w.dln_tmp);
@@ -785,6 +796,7 @@ void cotr_destroy(cotr_model* m) {
     for (float** b : fbufs) ws_free_f32(b);
     if (m->host_stream) cudaStreamDestroy(m->host_stream);
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+    preprocessor_destroy(m->pre);
     for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
     delete m;
 }
@@ -831,12 +843,14 @@ int ensure_stage(cotr_model* m, int B, int Q) {
     const size_t q_elems = (size_t)B * Q * 2;
     if (img_elems > w.img_stage_elems) {
         COTR_CHECK_CUDA(cudaDeviceSynchronize());
+        drop_graphs(m);
         ws_free_f32(&w.img_stage);
         if (ws_alloc_f32(&w.img_stage, img_elems)) return 1;
         w.img_stage_elems = img_elems;
     }
     if (q_elems > w.q_stage_elems) {
         COTR_CHECK_CUDA(cudaDeviceSynchronize());
+        drop_graphs(m);
         ws_free_f32(&w.q_stage); ws_free_f32(&w.pred_stage);
         if (ws_alloc_f32(&w.q_stage, q_elems ? q_elems : 2) || ws_alloc_f32(&w.pred_stage, q_elems ? q_elems : 2)) return 1;
         w.q_stage_elems = q_elems;
@@ -847,6 +861,7 @@ int ensure_stage(cotr_model* m, int B, int Q) {
 int forward_eager(cotr_model* m, const float* img, const float* queries, int B, int Q, float* pred, cudaStream_t s) {
     if (m->own_ctx->max_pairs < B) {
         COTR_CHECK_CUDA(cudaDeviceSynchronize());
+        drop_graphs(m);
         cotr_context_destroy(m->own_ctx);
         m->own_ctx = nullptr;
         if (cotr_context_create(m, B, &m->own_ctx)) return 1;
@@ -934,6 +949,15 @@ int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries
     return 0;
 }
 
+int cotr_preprocess(cotr_model* m, const uint8_t* img_from_dev, int h_from, int w_from, const uint8_t* img_to_dev, int h_to,
+                    int w_to, const int32_t* rects_host, int n, float* canvas_dev, void* cuda_stream) {
+    COTR_CHECK(m != nullptr, "cotr_preprocess: null model");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    if (!m->pre) m->pre = preprocessor_create();
+    return preprocess_launch(m->pre, img_from_dev, h_from, w_from, img_to_dev, h_to, w_to, rects_host, n, canvas_dev,
+                             (cudaStream_t)cuda_stream);
+}
+
 int cotr_set_graph_mode(cotr_model* m, int enabled) {
     COTR_CHECK(m != nullptr, "cotr_set_graph_mode: null model");
     m->graph_mode = enabled != 0;
@@ -1005,6 +1029,7 @@ int cotr_set_gemm_path(cotr_model* m, int path) {
         cudaSetDevice(m->device);
         cudaDeviceSynchronize();
         for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+    preprocessor_destroy(m->pre);
         m->graphs.clear();
         m->graph_launches.clear();
         m->shapes_seen.clear();

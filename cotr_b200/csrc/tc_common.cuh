@@ -55,6 +55,11 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// named CTA barrier `id` (1..15; 0 is __syncthreads) over `threads` threads (a multiple of 32, whole warps)
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ---- thread-block cluster: barrier and distributed shared memory ------------------------------------------------
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }

@@ -28,30 +28,74 @@ def _is_open(task, zoom=None):
     return zoom is None or task.cur_zoom == zoom
 
 
+def _rect_of(task):
+    pf, pt = task.cur_job['patch_from'], task.cur_job['patch_to']
+    assert pf.w == pf.h and pt.w == pt.h
+    return (pf.x, pf.y, pf.w, pt.x, pt.y, pt.w)
+
+
 class SparseEngine():
-    def __init__(self, model, batch_size, mode='stretching'):
+    def __init__(self, model, batch_size, mode='stretching', device_preprocess=True):
         assert mode in ['stretching', 'tile']
         self.model = model
         self.batch_size = batch_size
         self.total_tasks = 0
         self.mode = mode
+        # When the model is the native one, the crops are resized / normalised on the device (bit-identical to the
+        # host PIL path, which remains the behaviour for any other model) - see COTR.preprocess_canvases.
+        self.device_preprocess = device_preprocess
+        self._dev_images = {}
+
+    # ---- device-side pixels --------------------------------------------------------------------------------
+    def _use_device_pixels(self, tasks):
+        if not (self.device_preprocess and getattr(self.model, 'supports_device_preprocess', False)):
+            return False
+        try:
+            if next(self.model.parameters()).device.type != 'cuda':
+                return False
+        except StopIteration:
+            return False
+        first = tasks[0]
+        for img in (first.image_from, first.image_to):
+            if not (isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3):
+                return False
+        return all(t.image_from is first.image_from and t.image_to is first.image_to for t in tasks)
+
+    def _device_image(self, img):
+        key = (id(img), img.shape)
+        hit = self._dev_images.get(key)
+        if hit is None or hit[0] is not img:
+            if len(self._dev_images) > 8:
+                self._dev_images.clear()
+            dev = next(self.model.parameters()).device
+            hit = (img, torch.from_numpy(np.ascontiguousarray(img)).to(dev))
+            self._dev_images[key] = hit
+        return hit[1]
+
+    def _device_canvases(self, tasks):
+        rects = np.array([_rect_of(t) for t in tasks], dtype=np.int32)
+        return self.model.preprocess_canvases(self._device_image(tasks[0].image_from), self._device_image(tasks[0].image_to), rects)
 
     # ---- batching ------------------------------------------------------------------------------------------
     def form_batch(self, tasks, zoom=None):
         """First `batch_size` open tasks (optionally at one zoom level) -> stacked canvases and queries (:25-45)."""
-        task_ref, imgs, queries = [], [], []
+        chosen = []
         for t in tasks:
-            if not _is_open(t, zoom):
-                continue
+            if _is_open(t, zoom):
+                chosen.append(t)
+                if len(chosen) >= self.batch_size:
+                    break
+        if not chosen:
+            return [], [], []
+        if self._use_device_pixels(chosen):
+            queries = [t.get_task_fast()[1] for t in chosen]           # geometry + query only
+            return chosen, self._device_canvases(chosen), torch.stack(queries)
+        imgs, queries = [], []
+        for t in chosen:
             img, query = t.get_task()
-            task_ref.append(t)
             imgs.append(img)
             queries.append(query)
-            if len(task_ref) >= self.batch_size:
-                break
-        if not task_ref:
-            return [], [], []
-        return task_ref, torch.stack(imgs), torch.stack(queries)
+        return chosen, torch.stack(imgs), torch.stack(queries)
 
     def infer_batch(self, img_batch, query_batch):
         """(n,3,256,512) + (n,1,2) -> (n,2) numpy; NaN raises like the reference (:47-56)."""
@@ -233,9 +277,10 @@ class SparseEngine():
 class FasterSparseEngine(SparseEngine):
     """Nearby tasks share one network context: faster, slightly less accurate (:267-427)."""
 
-    def __init__(self, model, batch_size, mode='stretching', max_load=256):
-        super().__init__(model, batch_size, mode=mode)
+    def __init__(self, model, batch_size, mode='stretching', max_load=256, device_preprocess=True):
+        super().__init__(model, batch_size, mode=mode, device_preprocess=device_preprocess)
         self.max_load = max_load
+        self._squad_pixels_on_device = False
 
     def infer_batch_grouped(self, img_batch, query_batch):
         device = next(self.model.parameters()).device
@@ -264,7 +309,7 @@ class FasterSparseEngine(SparseEngine):
 
         f_l, f_r, f_u, f_d = safe_box(info['patch_from'])
         t_l, t_r, t_u, t_d = safe_box(info['patch_to'])
-        img, query = pilot.get_task()
+        img, query = pilot.get_task_fast() if self._squad_pixels_on_device else pilot.get_task()
         assert pilot.submitted == True
         members, queries = [pilot], [query]
         bookkeeping[pilot_id] = False
@@ -283,6 +328,8 @@ class FasterSparseEngine(SparseEngine):
     def form_grouped_batch(self, zoom, tasks):
         """Up to batch_size squads; queries zero-padded to the longest squad (:339-369)."""
         tasks_map, task_ids = self.get_tasks_map(zoom, tasks)
+        candidates = [tasks[i] for i in task_ids] if len(task_ids) else []
+        self._squad_pixels_on_device = bool(candidates) and self._use_device_pixels(candidates)
         shuffle = np.random.permutation(tasks_map.shape[0])
         tasks_map = np.take(tasks_map, shuffle, axis=0)
         task_ids = np.take(task_ids, shuffle, axis=0)
@@ -302,7 +349,11 @@ class FasterSparseEngine(SparseEngine):
             return [], [], []
         longest = max(q.shape[1] for q in queries)
         queries = [torch.cat([q, torch.zeros([1, longest - q.shape[1], 2])], axis=1) for q in queries]
-        return task_ref, torch.stack(imgs), torch.cat(queries)
+        if self._squad_pixels_on_device:
+            img_batch = self._device_canvases([squad[0] for squad in task_ref])      # one context per pilot
+        else:
+            img_batch = torch.stack(imgs)
+        return task_ref, img_batch, torch.cat(queries)
 
     def cotr_corr_multiscale(self, img_a, img_b, zoom_ins=[1.0], converge_iters=1, max_corrs=1000, queries_a=None,
                              return_idx=False, force=False, return_tasks_only=False, areas=None):

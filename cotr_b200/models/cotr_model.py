@@ -227,7 +227,18 @@ class COTR(nn.Module):
         q = self._queries(queries, x.shape[0])
         return {'pred_corrs': self.native().forward(x, q)}
 
-    # ---- extensions used by cotr_b200.inference (context reuse across query batches) --------------------
+    # ---- extensions used by cotr_b200.inference ---------------------------------------------------------
+    supports_device_preprocess = True
+
+    @torch.no_grad()
+    def preprocess_canvases(self, img_from_u8, img_to_u8, rects):
+        """Device-side `RefinementTask.get_task` pixels: uint8 HWC CUDA images + (n,6) int32 rectangles
+        [x_from, y_from, size_from, x_to, y_to, size_to] -> (n,3,256,512) normalised fp32 canvases, bit-identical to
+        the PIL resize + to_tensor + normalize of the reference (cotr_preprocess in include/cotr_b200.h)."""
+        assert img_from_u8.dtype == torch.uint8 and img_to_u8.dtype == torch.uint8
+        assert img_from_u8.ndim == 3 and img_from_u8.shape[2] == 3 and img_to_u8.ndim == 3 and img_to_u8.shape[2] == 3
+        return self.native().preprocess(img_from_u8.contiguous(), img_to_u8.contiguous(), rects)
+
     @torch.no_grad()
     def encode_context(self, samples):
         x = self._canvas(samples)

@@ -79,6 +79,15 @@ int cotr_forward(cotr_model* m, const float* img_dev, const float* queries_dev, 
 int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries_host, int B, int Q,
                       float* pred_host);
 
+/* Device-side replacement of the host work of RefinementTask.get_task (COTR/inference/refinement_task.py:105-120) and
+ * of the canvas construction in inference_helper.py:108-113: for each of the n tasks crop a square patch out of the
+ * "from" image and one out of the "to" image (uint8 HWC, 3 channels, DEVICE memory, uploaded once per engine call),
+ * resize both to 256x256 with Pillow's antialiased bilinear filter (bit-exact), put them side by side and apply
+ * to_tensor + normalize(mean (0.485,0.456,0.406), std (0.229,0.224,0.225)).  rects_host: n x 6 int32 HOST array
+ * [x_from, y_from, size_from, x_to, y_to, size_to]; canvas_dev: (n,3,256,512) fp32 DEVICE output. */
+int cotr_preprocess(cotr_model* m, const uint8_t* img_from_dev, int h_from, int w_from, const uint8_t* img_to_dev, int h_to,
+                    int w_to, const int32_t* rects_host, int n, float* canvas_dev, void* cuda_stream);
+
 /* cotr_forward / cotr_forward_host replay a CUDA graph per (B,Q) shape (captured on the second call with that shape;
  * inputs / outputs pass through internal staging buffers so the graph's addresses stay fixed).  0 disables it. */
 int cotr_set_graph_mode(cotr_model* m, int enabled);

@@ -1,0 +1,124 @@
+"""GPU: the zoom-in engines (cotr_b200.inference) driving the native sm_100a model, against the same engines driving
+the CPU oracle.  The loop is discontinuous in the network output (integer crop corners, accept / reject thresholds),
+so the comparison is reported in pixels on forced queries (SURVEY.md section 7 "what engine-level parity can mean")."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from oracle import cotr_oracle, fixtures
+from oracle.fake_model import synthetic_image
+
+pytestmark = pytest.mark.gpu
+
+
+class OracleCOTR(nn.Module):
+    """The CPU oracle behind the model(img, queries)['pred_corrs'] contract (test-side only)."""
+
+    def __init__(self, sd):
+        super().__init__()
+        self.anchor = nn.Parameter(torch.zeros(1), requires_grad=False)
+        self.sd = cotr_oracle.cast_state_dict(sd, torch.float32)
+
+    @torch.no_grad()
+    def forward(self, img, queries):
+        return {'pred_corrs': cotr_oracle.forward(self.sd, img.cpu(), queries.cpu(), torch.float32)}
+
+
+@pytest.fixture(scope="module")
+def models(built_lib):
+    from cotr_b200.models import build_model
+    sd = fixtures.make_state_dict(0)
+    native = build_model(None)
+    native.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return native.cuda().eval(), OracleCOTR(sd)
+
+
+def test_dense_flow_matches_oracle(models):
+    """cotr_flow: one dense pass (131 072 grid queries) per direction on a square pair."""
+    from cotr_b200.inference.inference_helper import cotr_flow
+    native, oracle = models
+    img_a = synthetic_image(31, 256, 256)
+    img_b = synthetic_image(32, 256, 256)
+    got = cotr_flow(native, img_a, img_b)
+    ref = cotr_flow(oracle, img_a, img_b)
+    for g, r, name in zip((got[0], got[1], got[3], got[4]), (ref[0], ref[1], ref[3], ref[4]), ("corr_a", "conf_a", "corr_b", "conf_b")):
+        assert g.shape == r.shape
+        # dense maps are in [-1,1] canvas units: 1e-3 there is the north-star tolerance (x2 for the [-1,1] scaling)
+        assert np.abs(g - r).max() < 4e-3, name
+
+
+def test_sparse_engine_matches_oracle_in_pixels(models, capsys):
+    from cotr_b200.inference.sparse_engine import SparseEngine
+    from cotr_b200.utils.utils import fix_randomness
+    native, oracle = models
+    img_a = synthetic_image(33, 320, 320)
+    img_b = synthetic_image(34, 288, 288)
+    rs = np.random.RandomState(3)
+    queries = np.stack([rs.uniform(20, 300, 12), rs.uniform(20, 300, 12)], axis=1)
+    zooms = np.linspace(0.5, 0.125, 3)
+    out = []
+    for model in (native, oracle):
+        fix_randomness(0)
+        corrs = SparseEngine(model, 8, mode='tile').cotr_corr_multiscale(
+            img_a, img_b, zooms, 1, max_corrs=12, queries_a=queries.copy(), force=True)
+        out.append(corrs)
+    got, ref = out
+    assert got.shape == ref.shape == (12, 4)
+    assert np.array_equal(got[:, :2], ref[:, :2])                 # the forced source points
+    diff = np.linalg.norm(got[:, 2:] - ref[:, 2:], axis=1)
+    # a 1e-3 deviation of the network output is 0.3 px at the coarsest level and shrinks with the zoom
+    assert np.median(diff) < 0.25 and diff.max() < 1.5, diff
+
+
+def test_device_preprocess_is_bit_identical_to_pillow(models):
+    """cotr_preprocess (crop + Pillow-exact antialiased resize + to_tensor + normalize on the device) against the
+    host path of the reference (PIL resize, torchvision to_tensor / normalize) - every pixel, every bit."""
+    from cotr_b200.inference.inference_helper import _to_network_canvas
+    native, _ = models
+    img_a = synthetic_image(41, 783, 1064)
+    img_b = synthetic_image(42, 1053, 689)
+    rs = np.random.RandomState(7)
+    rects = []
+    for size_a, size_b in [(782, 688), (390, 344), (276, 256), (256, 162), (162, 48), (48, 2), (600, 100), (254, 258)]:
+        xa = rs.randint(0, img_a.shape[1] - size_a + 1); ya = rs.randint(0, img_a.shape[0] - size_a + 1)
+        xb = rs.randint(0, img_b.shape[1] - size_b + 1); yb = rs.randint(0, img_b.shape[0] - size_b + 1)
+        rects.append((xa, ya, size_a, xb, yb, size_b))
+    rects = np.array(rects, dtype=np.int32)
+    dev = native.preprocess_canvases(torch.from_numpy(img_a).cuda(), torch.from_numpy(img_b).cuda(), rects).cpu()
+    for i, (xa, ya, sa, xb, yb, sb) in enumerate(rects):
+        ref = _to_network_canvas(img_a[ya:ya + sa, xa:xa + sa], img_b[yb:yb + sb, xb:xb + sb])
+        assert torch.equal(dev[i], ref), (i, (dev[i] - ref).abs().max().item())
+
+
+def test_engine_device_pixels_equal_host_pixels(models):
+    """The engines give identical correspondences whether the crops are resized on the device or by PIL on the host."""
+    from cotr_b200.inference.sparse_engine import FasterSparseEngine, SparseEngine
+    from cotr_b200.utils.utils import fix_randomness
+    native, _ = models
+    img_a = synthetic_image(43, 300, 400)
+    img_b = synthetic_image(44, 360, 288)
+    rs = np.random.RandomState(9)
+    queries = np.stack([rs.uniform(5, 395, 24), rs.uniform(5, 295, 24)], axis=1)
+    zooms = np.linspace(0.5, 0.0625, 4)
+    for engine_cls, kw in ((SparseEngine, {}), (FasterSparseEngine, {"max_load": 8})):
+        results = []
+        for on_device in (True, False):
+            fix_randomness(0)
+            eng = engine_cls(native, 8, mode='tile', device_preprocess=on_device, **kw)
+            results.append(eng.cotr_corr_multiscale(img_a, img_b, zooms, 2, max_corrs=24, queries_a=queries.copy(), force=True))
+        assert results[0].shape == results[1].shape
+        assert np.array_equal(results[0], results[1])
+
+
+def test_context_reuse_in_corr_base(models):
+    """cotr_corr_base uses encode_context/decode on the native model (one context, two decodes)."""
+    from cotr_b200.inference.inference_helper import cotr_corr_base
+    native, oracle = models
+    img_a = synthetic_image(35, 256, 256)
+    img_b = synthetic_image(36, 256, 256)
+    rs = np.random.RandomState(4)
+    q = np.stack([rs.uniform(5, 250, 20), rs.uniform(5, 250, 20)], axis=1)
+    got = cotr_corr_base(native, img_a, img_b, q.copy())
+    ref = cotr_corr_base(oracle, img_a, img_b, q.copy())
+    assert np.abs(got - ref).max() < 0.6          # pixels: 1e-3 * 2 * 256 = 0.5 px per axis at full scale

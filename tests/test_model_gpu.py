@@ -148,3 +148,26 @@ def test_weights_reload_repacks(built_lib):
     assert (a - b).abs().max().item() > 1e-3
     ref = cotr_oracle.forward(fixtures.make_state_dict(3), img, queries, torch.float32)
     assert (b.cpu() - ref).abs().max().item() < TOL
+
+
+def test_graph_replay_survives_workspace_growth(built_lib):
+    """A shape's captured graph embeds workspace addresses; a later, larger shape reallocates the workspace.  The
+    earlier shape must still replay correctly (graphs are dropped and re-captured), bit-identical to its first run."""
+    m = _build(fixtures.make_state_dict(0))
+    img1, q1 = fixtures.make_inputs(21, 1, 64)
+    img4, q4 = fixtures.make_inputs(22, 4, 64)
+    imgq, qq = fixtures.make_inputs(23, 1, 5000)
+    t1, u1 = torch.from_numpy(img1).cuda(), torch.from_numpy(q1).cuda()
+    t4, u4 = torch.from_numpy(img4).cuda(), torch.from_numpy(q4).cuda()
+    tq, uq = torch.from_numpy(imgq).cuda(), torch.from_numpy(qq).cuda()
+    first = m(t1, u1)["pred_corrs"].clone()                # eager
+    assert torch.equal(m(t1, u1)["pred_corrs"], first)     # captured
+    assert torch.equal(m(t1, u1)["pred_corrs"], first)     # replayed
+    big = [m(t4, u4)["pred_corrs"].clone() for _ in range(3)]      # encoder workspace + staging grow
+    assert torch.equal(big[0], big[1]) and torch.equal(big[0], big[2])
+    assert torch.equal(m(t1, u1)["pred_corrs"], first)
+    many = [m(tq, uq)["pred_corrs"].clone() for _ in range(3)]     # decoder workspace + query staging grow
+    assert torch.equal(many[0], many[1]) and torch.equal(many[0], many[2])
+    assert torch.equal(m(t1, u1)["pred_corrs"], first)
+    assert torch.equal(m(t4, u4)["pred_corrs"], big[0])
+    torch.cuda.synchronize()

@@ -132,6 +132,54 @@ def gemm_timeline():
                   f" epi done {r[21]} end {r[60]}", flush=True)
 
 
+def backbone_timeline():
+    """The same timeline for the backbone's heavy shapes: stem (7x7 on the fp32 canvas), layer1 conv3 (K=64 with a
+    residual and 8 MB of output), layer1 3x3, layer2 conv1."""
+    import ctypes
+    import torch
+    from cotr_b200 import capi
+    g = torch.Generator(device="cpu").manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    ts = torch.zeros(64 * 1024, dtype=torch.int64, device="cuda")
+
+    def show(tag, nchunks, ctas=(0, 1, 200)):
+        t = ts.cpu().view(-1, 64)
+        for cta in ctas:
+            r = t[cta].tolist()
+            if r[60] == 0:
+                continue
+            n = min(6, nchunks)
+            print(f"  {tag} cta{cta}: setup {r[1]} fetch0 {r[2]} | loader got/pub " +
+                  " ".join(f"{r[3 + 2 * i]}/{r[4 + 2 * i]}" for i in range(n)) +
+                  " | mma sawA/issued " + " ".join(f"{r[24 + 2 * i]}/{r[25 + 2 * i]}" for i in range(n)) +
+                  f" | final commit {r[41]} acc ready {r[20]} | chunk0 acc/apply/emit {r[30]}/{r[31]}/{r[32]} chunk1 {r[34]}/{r[35]}/{r[36]}"
+                  f" before drain {r[38]} epi done {r[21]} end {r[60]}", flush=True)
+
+    def run(tag, nchunks, fn):
+        for rep in range(3):
+            ts.zero_()
+            capi.lib().cotr_debug_set_timestamps(ctypes.c_void_p(ts.data_ptr()))
+            torch.cuda.synchronize()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            fn()
+        capi.lib().cotr_debug_set_timestamps(None)
+        show(tag, nchunks)
+
+    img = rnd(1, 3, 256, 512).cuda(); w = (rnd(64, 3, 7, 7) * 0.1).permute(0, 2, 3, 1).reshape(64, -1).contiguous().numpy()
+    bias64 = rnd(64).cuda()
+    run("stem 32768x64x147", 3, lambda: capi.test_gemm(0, img, w, bias=bias64, relu=True, a_mode=2, M=2 * 128 * 128,
+                                                        conv=dict(H=256, W=256, C=3, OH=128, OW=128, KH=7, KW=7, stride=2, pad=3)))
+    A = rnd(8192, 64).cuda(); W = (rnd(256, 64) * 0.1).numpy(); b = rnd(256).cuda(); res = rnd(8192, 256).cuda()
+    run("l1.conv3 8192x256x64 +res+relu", 1, lambda: capi.test_gemm(0, A, W, bias=b, residual=res, relu=True))
+    A2 = rnd(8192, 256).cuda(); W2 = (rnd(64, 256) * 0.1).numpy()
+    run("l1.conv1 8192x64x256 relu", 4, lambda: capi.test_gemm(0, A2, W2, bias=bias64, relu=True))
+    x = rnd(2, 64, 64, 64).permute(0, 2, 3, 1).contiguous().cuda(); w3 = (rnd(64, 64, 3, 3) * 0.05).permute(0, 2, 3, 1).reshape(64, -1).contiguous().numpy()
+    run("l1.conv2 3x3 8192x64x576", 9, lambda: capi.test_gemm(0, x, w3, bias=bias64, relu=True, a_mode=1, M=8192,
+                                                               conv=dict(H=64, W=64, C=64, OH=64, OW=64, KH=3, KW=3, stride=1, pad=1)))
+    A3 = rnd(2048, 128).cuda(); W3 = (rnd(512, 128) * 0.1).numpy(); b3 = rnd(512).cuda(); res3 = rnd(2048, 512).cuda()
+    run("l2.conv3 2048x512x128 +res+relu", 2, lambda: capi.test_gemm(0, A3, W3, bias=b3, residual=res3, relu=True))
+
+
 def launch_profile():
     """Per-launch CUDA-event durations of one eager forward (B=1, Q=1024), library profiler."""
     import torch
@@ -260,6 +308,8 @@ def run_stage(name):
         launch_profile()
     elif name == "gemm_timeline":
         gemm_timeline()
+    elif name == "backbone_timeline":
+        backbone_timeline()
     elif name == "tc_precision":
         tc_precision()
     else:
