@@ -27,10 +27,19 @@ __device__ __forceinline__ ARow decode_a_row(const GemmParams& p, int m) {
         r.off = (size_t)row * p.lda;
     } else {
         const int ohw = p.OH * p.OW;
-        const int n = m / ohw;
-        const int rem = m - n * ohw;
-        const int oh = rem / p.OW;
-        const int ow = rem - oh * p.OW;
+        int n, oh, ow;
+        if (((ohw & (ohw - 1)) | (p.OW & (p.OW - 1))) == 0) {      // every feature map of this network: powers of two
+            const int s_img = 31 - __clz(ohw), s_row = 31 - __clz(p.OW);
+            n = m >> s_img;
+            const int rem = m & (ohw - 1);
+            oh = rem >> s_row;
+            ow = rem & (p.OW - 1);
+        } else {
+            n = m / ohw;
+            const int rem = m - n * ohw;
+            oh = rem / p.OW;
+            ow = rem - oh * p.OW;
+        }
         r.ih0 = oh * p.stride - p.pad;
         r.iw0 = ow * p.stride - p.pad;
         if (p.a_mode == A_CONV_NHWC) {

@@ -34,6 +34,7 @@ void set_error(const char* fmt, ...);
 // (or still reads).  At batch 1 the forward is ~135 latency-bound launches, so hiding launch + prologue matters.
 // ---------------------------------------------------------------------------------------------------------------
 extern int g_use_pdl;
+extern long long* g_tc_timestamps;   // debug timeline buffer of the tcgen05 kernels (cotr_debug_set_timestamps), else null
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -19,10 +19,12 @@
 //     mbarrier (cp.async.mbarrier.arrive.noinc) - no registers, no conversion, up to kStages chunks in flight.  Only
 //     the 7x7 stem reads the caller's fp32 canvas and converts in registers;
 //   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma (N = BN) and owns TMEM;
-//   * warps 0-3 then run the epilogue out of TMEM (software pipelined: the global operands of chunk c+1 are in flight
-//     while chunk c is combined): bias / constant add-matrix / residual / ReLU, or the fused residual + LayerNorm over
-//     the full 256-wide row (each thread owns one row, so no cross-thread reduction), and write split16 (optionally
-//     with the value-projection blocks transposed for the attention kernels).
+//   * all 8 warps then run the epilogue out of TMEM (the epilogue is instruction-issue bound, so it gets two warps per
+//     scheduler: warp w owns TMEM lanes 32 (w % 4).. and the column half w / 4 of the tile; software pipelined: the
+//     global operands of chunk c+1 are in flight while chunk c is combined): bias / constant add-matrix / residual /
+//     ReLU, or - on warps 0-3 only - the fused residual + LayerNorm over the full 256-wide row (each thread owns one
+//     row, so no cross-thread reduction), and write split16 (optionally with the value-projection blocks transposed
+//     for the attention kernels).
 // The kernel is templated on the A-operand addressing mode so that each instantiation carries exactly one loader
 // (an earlier all-modes-in-one kernel was ~30k SASS instructions and instruction-cache bound, profiles/r01_*).
 #include <cmath>
@@ -57,14 +59,21 @@ struct Cfg {
     static constexpr uint32_t kStage = 2 * kAPlane + 2 * kBPlane;
     static constexpr int kStagesRaw = (int)((227u * 1024u - 3072u) / kStage);
     static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;
-    // TMEM accumulator slots of BN columns each: kMain slots take the hi*hi products round-robin over K steps (the
-    // truncating accumulate is a systematic bias that grows with the chain length and adds up across layers), kCorr
-    // slots take the small lo*hi / hi*lo products.  Consecutive MMAs never chain on the same accumulator where TMEM
-    // allows (a chained MMA waits ~110 cycles for its predecessor).
-    static constexpr int kMain = BN >= 256 ? 1 : (BN >= 128 ? 2 : 4);   // BN = 16 / 32 / 64: 4
-    static constexpr int kCorr = BN >= 256 ? 1 : 2;
-    static constexpr int kSlots = kMain + kCorr;
-    static constexpr uint32_t kAccCols = kSlots * BN;
+    // TMEM accumulators: kMain slots take the hi*hi products round-robin over K steps (the truncating accumulate is a
+    // systematic bias that grows with the chain length and adds up across layers), the small lo*hi / hi*lo products
+    // go to separate columns.  Consecutive MMAs never chain on the same accumulator where TMEM allows (a chained MMA
+    // waits ~110 cycles for its predecessor).
+    // Narrow tiles (BN <= 64) are bound by the ~60-cycle issue cost of an M = 128 MMA, not by its math, so there the
+    // weight planes are used STACKED: B_hi and B_lo are adjacent in the stage, one MMA of N = 2 BN forms
+    // A_hi * [B_hi; B_lo] (main | hi*lo correction in adjacent columns) and a second one of N = BN adds A_lo * B_hi:
+    // two MMAs per K step instead of three.
+    static constexpr bool kStacked = BN <= 64;
+    static constexpr int kMain = BN >= 256 ? 1 : (BN >= 128 ? 2 : (BN == 64 ? 3 : 4));
+    static constexpr int kCorr = BN >= 256 ? 1 : 2;                     // separate correction slots of BN columns
+    static constexpr uint32_t kMainStride = kStacked ? 2u * BN : BN;    // stacked: [main | hi*lo] pairs
+    static constexpr uint32_t kCorrBase = kMain * kMainStride;
+    static constexpr uint32_t kAccCols = kCorrBase + kCorr * BN;
+    static constexpr int kSmall = kStacked ? kMain + kCorr : kCorr;     // 16-column loads of correction terms per chunk
     // epilogue staging (re-uses the pipeline stages): per warp 2 planes x 32 rows, row pitch padded by 16 bytes
     static constexpr uint32_t kOutPitch = BN * 2u + 16u;
     static constexpr uint32_t kWarpStaging = 2u * 32u * kOutPitch;
@@ -76,6 +85,14 @@ struct Cfg {
     static constexpr int kRing = kChunksW < 4 ? kChunksW : 4;          // epilogue operand prefetch depth
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
     static constexpr uint32_t kSmemBytes = kStages * kStage + 2048;     // + alignment slack + barriers
+    // split-K: the leader CTA of a cluster receives one fp32 partial tile per peer behind the barriers (a dedicated
+    // region, so peers may push while the leader's pipeline is still running); rows of BN * 4 bytes, 16-byte pieces
+    // XOR-swizzled by row % 8 (thread-per-row accesses would otherwise all land in the same banks)
+    static constexpr uint32_t kPartOffset = kStages * kStage + 256;
+    static constexpr uint32_t kPartPitch = BN * 4u;
+    static constexpr uint32_t kPartBytes = 128u * kPartPitch;
+    static constexpr int kMaxSplit = BN <= 32 ? 4 : (BN <= 64 ? 2 : 1);
+    static_assert(kSmemBytes + (kMaxSplit - 1) * kPartBytes <= 227u * 1024u, "split-K partial tiles do not fit");
     static_assert(kStages >= 2, "pipeline needs at least two stages");
     static_assert(kAccCols <= 512, "TMEM has 512 columns");
     static_assert(kStage % 1024 == 0, "stages must stay 1024-byte aligned for SWIZZLE_128B");
@@ -92,7 +109,7 @@ template <int BN, bool LN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p, const int npad, long long* __restrict__ ts) {
     using C = Cfg<BN>;
     // debug timeline (ts != null): slot layout documented in tools/bringup.py::gemm_timeline
-    long long* my_ts = ts ? ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+    long long* my_ts = ts ? ts + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
     const long long t_start = ts ? clock64() : 0;
 #define COTR_TS(slot) do { if (my_ts) my_ts[(slot)] = clock64() - t_start; } while (0)
     extern __shared__ uint8_t smem_raw[];
@@ -103,13 +120,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     uint64_t* full_b = bars + C::kStages;
     uint64_t* empty = bars + 2 * C::kStages;
     uint64_t* accum_full = bars + 3 * C::kStages;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
+    uint64_t* part_full = bars + 3 * C::kStages + 1;       // split-K leader: all peers' partial tiles have landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     // split-K: gridDim.z CTAs of one cluster (cluster dims 1 x 1 x gridDim.z) share the output tile; CTA z walks the
-    // K chunks [it0, it0 + KC) and CTAs z > 0 hand their partial sums to CTA 0 through distributed shared memory.
+    // K chunks [it0, it0 + KC) and CTAs z > 0 hand their partial sums to CTA 0 through distributed shared memory:
+    // asynchronous remote stores (st.async) that complete transaction bytes on an mbarrier of the leader, so the
+    // hand-over costs one store latency and no cluster-wide barrier (measured: ~2.3k cycles for barrier.cluster).
     const int ksplit = gridDim.z;
     const int kz = blockIdx.z;
     const int KC = ((p.K + BK - 1) / BK) / ksplit;
@@ -122,13 +142,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             mbar_init(&empty[s], 1);
         }
         mbar_init(accum_full, 1);
+        mbar_init(part_full, 1);
         mbar_fence_init();
+        if (ksplit > 1 && kz == 0) mbar_arrive_expect_tx(part_full, (uint32_t)(ksplit - 1) * C::kPartBytes);
     }
     if (warp == 5) tmem_alloc(tmem_ptr, C::kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // split-K: tell the cluster that this CTA runs and its barriers exist (waited for just before the first remote access)
+    if (ksplit > 1) cluster_arrive();
     if (threadIdx.x == 0) COTR_TS(1);
 
     if (warp < 4) {
@@ -246,9 +270,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         // ================= MMA issuer ===========================================================================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
+            constexpr uint32_t idesc2 = make_idesc_f16_f32(BM, C::kStacked ? 2 * BN : BN);
             const uint32_t hi_word = desc_hi_sw128();
-            const uint32_t corr_a = tmem_base + (uint32_t)C::kMain * BN;
-            const uint32_t corr_b = tmem_base + (uint32_t)(C::kMain + C::kCorr - 1) * BN;
+            const uint32_t corr_a = tmem_base + C::kCorrBase;
+            const uint32_t corr_b = tmem_base + C::kCorrBase + (uint32_t)(C::kCorr - 1) * BN;
 #pragma unroll 1
             for (int it = 0; it < KC; ++it) {
                 const int s = it % C::kStages;
@@ -268,10 +293,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     const uint64_t dal = make_desc(a_h0 + (kAPlane >> 4) + 2 * ks, hi_word);
                     const uint64_t dbh = make_desc(b_h0 + 2 * ks, hi_word);
                     const uint64_t dbl = make_desc(b_h0 + (C::kBPlane >> 4) + 2 * ks, hi_word);
-                    const uint32_t main_col = tmem_base + (uint32_t)(g % C::kMain) * BN;
-                    umma_f16_ss(corr_a, dal, dbh, idesc, g != 0);
-                    umma_f16_ss(main_col, dah, dbh, idesc, g >= C::kMain);
-                    umma_f16_ss(corr_b, dah, dbl, idesc, C::kCorr == 1 ? true : g != 0);
+                    const uint32_t main_col = tmem_base + (uint32_t)(g % C::kMain) * C::kMainStride;
+                    if constexpr (C::kStacked) {
+                        // the descriptor of B_hi with N = 2 BN runs on into the B_lo plane (next 8-row groups)
+                        umma_f16_ss(tmem_base + C::kCorrBase + (uint32_t)(g & 1) * BN, dal, dbh, idesc, g >= 2);
+                        umma_f16_ss(main_col, dah, dbh, idesc2, g >= C::kMain);
+                    } else {
+                        umma_f16_ss(corr_a, dal, dbh, idesc, g != 0);
+                        umma_f16_ss(main_col, dah, dbh, idesc, g >= C::kMain);
+                        umma_f16_ss(corr_b, dah, dbl, idesc, C::kCorr == 1 ? true : g != 0);
+                    }
                 }
                 umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
                 if (it < 8) COTR_TS(25 + 2 * it);
@@ -286,9 +317,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     // Warps 0-3 arrive here when their last copies are issued, warps 4/5 when the last TMA / MMA is issued, 6/7 at once.
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = warp >> 2;              // column half of the tile it handles
-    if (half >= C::kEpiHalves) {
-        if (ksplit > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
-    } else {
+    if (ksplit > 1) cluster_wait();          // every CTA of the cluster has started (long ago by now)
+    if (half < C::kEpiHalves) {
         if (warp >= 4) pdl_wait();           // residual / add operands come from the previous kernels
         const int cbeg = half * C::kChunksW * 16;
         const int row = m0 + ew * 32 + lane;
@@ -345,31 +375,53 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         };
         // v[0..15] = acc_scale * (sum over all accumulators of columns [c, c+16)); all TMEM loads of the chunk are
         // issued back to back and waited for once.
-        constexpr uint32_t kPartPitch = BN * 4u + 16u;            // fp32 partial tile rows, padded
-        constexpr uint32_t kPartBytes = 128u * kPartPitch;
-        constexpr uint32_t kPartOffset = 4u * C::kWarpStaging;    // behind the output staging area
-        auto load_acc = [&](int c, float (&v)[16]) {
-            uint32_t r[C::kSlots][16];
-            __syncwarp();
+        constexpr uint32_t kPartPitch = C::kPartPitch, kPartBytes = C::kPartBytes, kPartOffset = C::kPartOffset;
+        const uint32_t part_row = (uint32_t)(ew * 32 + lane) * kPartPitch;     // this thread's row of a partial tile
+        const uint32_t part_swz = (uint32_t)(lane & 7);                        // == row % 8
+        // v = sum over all accumulators of columns [c, c+16), unscaled: the correction terms first (small), then the
+        // main slots, RN adds; the TMEM loads of each group are issued back to back and waited for once.
+        auto sum_acc = [&](int c, float (&v)[16]) {
+            float x[16];
+            {
+                uint32_t r[C::kSmall][16];
+                __syncwarp();
 #pragma unroll
-            for (int a = 0; a < C::kSlots; ++a) tmem_ld16_issue(trow + a * BN + c, r[a]);
+                for (int a = 0; a < C::kCorr; ++a) tmem_ld16_issue(trow + C::kCorrBase + a * BN + c, r[a]);
+                if constexpr (C::kStacked) {
 #pragma unroll
-            for (int a = 0; a < C::kSlots; ++a) tmem_ld16_fence(r[a]);
+                    for (int a = 0; a < C::kMain; ++a) tmem_ld16_issue(trow + a * C::kMainStride + BN + c, r[C::kCorr + a]);
+                }
+#pragma unroll
+                for (int a = 0; a < C::kSmall; ++a) tmem_ld16_fence(r[a]);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    x[j] = __uint_as_float(r[0][j]);
+#pragma unroll
+                    for (int a = 1; a < C::kSmall; ++a) x[j] += __uint_as_float(r[a][j]);
+                }
+            }
+            uint32_t r[C::kMain][16];
+#pragma unroll
+            for (int a = 0; a < C::kMain; ++a) tmem_ld16_issue(trow + a * C::kMainStride + c, r[a]);
+#pragma unroll
+            for (int a = 0; a < C::kMain; ++a) tmem_ld16_fence(r[a]);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(r[C::kMain][j]);                          // small terms first
-                if (C::kCorr == 2) x += __uint_as_float(r[C::kMain + 1][j]);
                 float y = __uint_as_float(r[0][j]);
 #pragma unroll
                 for (int a = 1; a < C::kMain; ++a) y += __uint_as_float(r[a][j]);
-                v[j] = x + y;
+                v[j] = x[j] + y;
             }
+        };
+        auto load_acc = [&](int c, float (&v)[16]) {
+            sum_acc(c, v);
             if (ksplit > 1 && kz == 0) {                  // leader: add the partial sums the peers pushed over DSMEM
-                const uint8_t* part = stage_base + kPartOffset + (uint32_t)(ew * 32 + lane) * kPartPitch + c * 4;
+                const uint8_t* part = stage_base + kPartOffset + part_row;
                 for (int peer = 0; peer < ksplit - 1; ++peer) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(part + (uint32_t)peer * kPartBytes + j * 4);
+                        const uint32_t piece = ((uint32_t)((c + j) >> 2) ^ part_swz) << 4;
+                        const float4 t4 = *reinterpret_cast<const float4*>(part + (uint32_t)peer * kPartBytes + piece);
                         v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
                     }
                 }
@@ -445,40 +497,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         tcgen05_fence_after();
         if (threadIdx.x == 0) COTR_TS(20);
         if (ksplit > 1) {
-            // barrier 1: every CTA's MMAs have retired, so the leader's pipeline stages are free to receive partials
-            cluster_arrive();
-            cluster_wait();
             if (kz != 0) {
-                const uint32_t local = smem_u32(stage_base) + kPartOffset + (uint32_t)(kz - 1) * kPartBytes +
-                                       (uint32_t)(ew * 32 + lane) * kPartPitch;
+                // the partial tiles have their own region in the leader's shared memory: push as soon as this CTA's
+                // MMAs have retired, whatever the leader is doing
+                const uint32_t local = smem_u32(stage_base) + kPartOffset + (uint32_t)(kz - 1) * kPartBytes + part_row;
                 const uint32_t remote = map_to_cta(local, 0);
+                const uint32_t remote_bar = map_to_cta(smem_u32(part_full), 0);
                 // unscaled partial sums travel; the leader applies acc_scale once in load_acc
 #pragma unroll 1
                 for (int ci = 0; ci < C::kChunksW; ++ci) {
                     const int c = cbeg + ci * 16;
-                    uint32_t r[C::kSlots][16];
-                    __syncwarp();
-#pragma unroll
-                    for (int a = 0; a < C::kSlots; ++a) tmem_ld16_issue(trow + a * BN + c, r[a]);
-#pragma unroll
-                    for (int a = 0; a < C::kSlots; ++a) tmem_ld16_fence(r[a]);
                     float v[16];
+                    sum_acc(c, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x = __uint_as_float(r[C::kMain][j]);
-                        if (C::kCorr == 2) x += __uint_as_float(r[C::kMain + 1][j]);
-                        float y = __uint_as_float(r[0][j]);
-#pragma unroll
-                        for (int a = 1; a < C::kMain; ++a) y += __uint_as_float(r[a][j]);
-                        v[j] = x + y;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) st_cluster_f32x4(remote + c * 4 + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 16; j += 4)
+                        st_async_f32x4(remote + (((uint32_t)((c + j) >> 2) ^ part_swz) << 4), v[j], v[j + 1], v[j + 2], v[j + 3], remote_bar);
                 }
+                if (threadIdx.x == 0) COTR_TS(22);
+            } else {
+                if (threadIdx.x == 0) COTR_TS(22);
+                mbar_wait(part_full, 0);             // (ksplit - 1) x 128 rows x BN floats have landed
+                if (threadIdx.x == 0) COTR_TS(23);
             }
-            // barrier 2: partials are visible in the leader's shared memory; the peers are done
-            cluster_arrive();
-            cluster_wait();
         }
         if (ksplit == 1 || kz == 0) {
 
@@ -490,12 +530,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 float v[16];
                 load_acc(c, v);
                 if (threadIdx.x == 0 && ci < 2) COTR_TS(30 + 4 * ci);
-                if (!tail) {
+                if (BN > 16 || !tail) {                          // (a ragged N only exists in the 16-wide instantiation)
                     apply(ops[ci % C::kRing], v);
                 } else {
-#pragma unroll 1
-                    for (int j = 0; j < 16 && nb + j < p.N; ++j)
-                        if (p.bias) v[j] += __ldg(p.bias + nb + j);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)                 // static indexing keeps v[] in registers
+                        if (p.bias && nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
                 }
                 if (p.relu) {
 #pragma unroll
@@ -575,7 +615,8 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        COTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, LN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+        COTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, LN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(C::kSmemBytes + (C::kMaxSplit - 1) * C::kPartBytes)));
         configured = true;
     }
     const int npad = tc_npad(p.N);
@@ -586,13 +627,14 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     if constexpr (!LN && BN <= 64 && MODE != LD_STEM) {
         const int kc = (p.K + BK - 1) / BK;
         const long long ctas = (long long)grid.x * grid.y;
-        if (!(g_tc_variant & 512) && kc >= 16) {
-            if (kc % 4 == 0 && ctas * 4 <= 160) ksplit = 4;
-            else if (kc % 2 == 0 && ctas * 2 <= 160) ksplit = 2;
+        if (!(g_tc_variant & 512) && kc >= ((g_tc_variant & 16384) ? 8 : 16)) {
+            if (C::kMaxSplit >= 4 && kc % 4 == 0 && ctas * 4 <= 160) ksplit = 4;
+            else if (C::kMaxSplit >= 2 && kc % 2 == 0 && ctas * 2 <= 160) ksplit = 2;
         }
     }
     grid.z = ksplit;
-    COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), C::kSmemBytes, s, ksplit, p, npad, g_tc_timestamps));
+    const size_t smem = C::kSmemBytes + (size_t)(ksplit - 1) * C::kPartBytes;      // the leader's partial-tile region
+    COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), smem, s, ksplit, p, npad, g_tc_timestamps));
     return 0;
 }
 
@@ -703,8 +745,12 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     // that still yields ~100 CTAs (148 SMs) wins; the narrow tiles trade tensor efficiency for parallelism and a
     // shorter per-CTA epilogue (the critical path of these latency-bound launches).
     const long long mt = (p.M + BM - 1) / BM;
-    if ((p.N % 128) == 0 && mt * (p.N / 128) >= 96) return launch_mode<128, false>(p, s);
-    if (mt * ((p.N + 63) / 64) >= 96 || p.a_mode == A_STEM_NCHW || (p.N % 32) != 0) return launch_mode<64, false>(p, s);
+    // bring-up knobs (cotr_debug_set_variant): bits 10-11 / 12-13 move the CTA-count thresholds of the 64 / 128 tiles
+    static const long long kThr[4] = {96, 48, 64, 148};
+    static const long long kThrWide[4] = {96, 48, 1 << 30, 148};
+    const long long thr64 = kThr[(g_tc_variant >> 10) & 3], thr128 = kThrWide[(g_tc_variant >> 12) & 3];
+    if ((p.N % 128) == 0 && mt * (p.N / 128) >= thr128) return launch_mode<128, false>(p, s);
+    if (mt * ((p.N + 63) / 64) >= thr64 || p.a_mode == A_STEM_NCHW || (p.N % 32) != 0) return launch_mode<64, false>(p, s);
     return launch_mode<32, false>(p, s);
 }
 

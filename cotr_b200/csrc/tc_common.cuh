@@ -73,6 +73,15 @@ __device__ __forceinline__ void st_cluster_f32x4(uint32_t cluster_addr, float a,
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Asynchronous 16-byte store into another CTA's shared memory that signals 16 bytes of transaction completion on an
+// mbarrier of that CTA (both addresses shared::cluster): the consumer waits on its own barrier, no cluster barrier.
+__device__ __forceinline__ void st_async_f32x4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
+
 // ---- bulk TMA: contiguous global -> shared, completion on an mbarrier --------------------------
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -1,5 +1,6 @@
 """A/B timing of the forward (B=1, Q=1024; B=8) under the library's bring-up switches, in one process.
-variant bits: 256 = no programmatic dependent launch, 512 = no split-K."""
+variant bits: 256 = no programmatic dependent launch, 512 = no split-K, 1024.. = tile-width thresholds
+(launch_gemm_tc in csrc/gemm_tc.cu)."""
 import os
 import sys
 
@@ -33,8 +34,11 @@ def measure(B, Q, n=30):
     return tot / n
 
 
+VARIANTS = [(0, "default"), (512, "no split-K"), (256, "no pdl")]
+if len(sys.argv) > 1:       # e.g. "0:default,1024:thr64=48,4096:thr128=48"
+    VARIANTS = [(int(x.split(":")[0]), x.split(":")[1]) for x in sys.argv[1].split(",")]
 for rep in range(2):
-    for variant, name in ((0, "pdl + split-K"), (512, "pdl, no split-K"), (256, "no pdl, split-K"), (768, "neither")):
+    for variant, name in VARIANTS:
         capi.lib().cotr_debug_set_variant(variant)
         nat.set_gemm_path(1); nat.set_gemm_path(0)          # drops the cached graphs
         print(f"  rep {rep} {name:18s}: B=1 Q=1024 {measure(1, 1024):.3f} ms | B=8 Q=1024 {measure(8, 1024, 10):.3f} ms | B=1 Q=16384 {measure(1, 16384, 10):.3f} ms", flush=True)

@@ -153,7 +153,7 @@ def backbone_timeline():
                   " ".join(f"{r[3 + 2 * i]}/{r[4 + 2 * i]}" for i in range(n)) +
                   " | mma sawA/issued " + " ".join(f"{r[24 + 2 * i]}/{r[25 + 2 * i]}" for i in range(n)) +
                   f" | final commit {r[41]} acc ready {r[20]} | chunk0 acc/apply/emit {r[30]}/{r[31]}/{r[32]} chunk1 {r[34]}/{r[35]}/{r[36]}"
-                  f" before drain {r[38]} epi done {r[21]} end {r[60]}", flush=True)
+                  f" before drain {r[38]} epi done {r[21]} end {r[60]} | cluster barrier in/out {r[22]}/{r[23]}", flush=True)
 
     def run(tag, nchunks, fn):
         for rep in range(3):
@@ -176,8 +176,44 @@ def backbone_timeline():
     x = rnd(2, 64, 64, 64).permute(0, 2, 3, 1).contiguous().cuda(); w3 = (rnd(64, 64, 3, 3) * 0.05).permute(0, 2, 3, 1).reshape(64, -1).contiguous().numpy()
     run("l1.conv2 3x3 8192x64x576", 9, lambda: capi.test_gemm(0, x, w3, bias=bias64, relu=True, a_mode=1, M=8192,
                                                                conv=dict(H=64, W=64, C=64, OH=64, OW=64, KH=3, KW=3, stride=1, pad=1)))
+    x3 = rnd(2, 16, 16, 256).cuda(); w33 = (rnd(256, 256, 3, 3) * 0.05).permute(0, 2, 3, 1).reshape(256, -1).contiguous().numpy()
+    b256 = rnd(256).cuda()
+    # split-K 4: grid (4, 8, 4); CTA 0 is a leader, CTA 32 the first peer (z = 1)
+    run("l3.conv2 3x3 512x256x2304 (split-K)", 9, lambda: capi.test_gemm(0, x3, w33, bias=b256, relu=True, a_mode=1, M=512,
+                                                                            conv=dict(H=16, W=16, C=256, OH=16, OW=16, KH=3, KW=3, stride=1, pad=1)))
+    show("   ... peers", 9, ctas=(32, 64))
+    A4 = rnd(512, 1024).cuda(); W4 = (rnd(256, 1024) * 0.05).numpy()
+    run("l3.conv1 512x256x1024 (split-K)", 4, lambda: capi.test_gemm(0, A4, W4, bias=b256, relu=True))
+    show("   ... peers", 4, ctas=(32, 64))
     A3 = rnd(2048, 128).cuda(); W3 = (rnd(512, 128) * 0.1).numpy(); b3 = rnd(512).cuda(); res3 = rnd(2048, 512).cuda()
     run("l2.conv3 2048x512x128 +res+relu", 2, lambda: capi.test_gemm(0, A3, W3, bias=b3, residual=res3, relu=True))
+
+
+def attn_timeline():
+    """clock64() timeline of the attention kernel.  Slots: 1 setup; 2 after griddepcontrol.wait; 3 staging issued;
+    4 S ready (softmax start); 5 row max done; 6+c P chunk c handed over; 14 O ready; 15 O stored; MMA thread: 20 Q/K
+    landed; 21 S issued; 22 V landed; 24+2c / 25+2c P chunk c seen / its MMAs issued; 60 end."""
+    import ctypes
+    import torch
+    from cotr_b200 import capi
+    g = torch.Generator(device="cpu").manual_seed(1)
+    ts = torch.zeros(64 * 1024, dtype=torch.int64, device="cuda")
+    for (nq, npairs) in [(512, 1), (1024, 1)]:
+        q = torch.randn(npairs * nq, 256, generator=g).cuda()
+        k = torch.randn(npairs * 512, 256, generator=g).cuda()
+        v = torch.randn(npairs * 512, 256, generator=g).cuda()
+        for rep in range(3):
+            ts.zero_()
+            capi.lib().cotr_debug_set_timestamps(ctypes.c_void_p(ts.data_ptr()))
+            capi.test_attention(0, q, k, v, nq, npairs)
+        capi.lib().cotr_debug_set_timestamps(None)
+        t = ts.cpu().view(-1, 64)
+        for cta in (0, 5):
+            r = t[cta].tolist()
+            print(f"  attention nq={nq} cta{cta}: setup {r[1]} pdl {r[2]} staged {r[3]} | mma: qk landed {r[20]} S issued {r[21]} v landed {r[22]} | "
+                  f"softmax: S ready {r[4]} max done {r[5]} P chunks " + " ".join(str(r[6 + c]) for c in range(8)) +
+                  " | mma saw/issued " + " ".join(f"{r[24 + 2 * c]}/{r[25 + 2 * c]}" for c in range(8)) +
+                  f" | O ready {r[14]} stored {r[15]} end {r[60]}", flush=True)
 
 
 def launch_profile():
@@ -308,6 +344,8 @@ def run_stage(name):
         launch_profile()
     elif name == "gemm_timeline":
         gemm_timeline()
+    elif name == "attn_timeline":
+        attn_timeline()
     elif name == "backbone_timeline":
         backbone_timeline()
     elif name == "tc_precision":
