@@ -85,14 +85,15 @@ struct Cfg {
     static constexpr int kRing = kChunksW < 4 ? kChunksW : 4;          // epilogue operand prefetch depth
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
     static constexpr uint32_t kSmemBytes = kStages * kStage + 2048;     // + alignment slack + barriers
-    // split-K: the leader CTA of a cluster receives one fp32 partial tile per peer behind the barriers (a dedicated
-    // region, so peers may push while the leader's pipeline is still running); rows of BN * 4 bytes, 16-byte pieces
-    // XOR-swizzled by row % 8 (thread-per-row accesses would otherwise all land in the same banks)
+    // split-K (reduce-scatter over the rows): every CTA of the cluster finishes 128 / ksplit rows of the tile and
+    // receives the other CTAs' fp32 partial rows behind the barriers (a dedicated region, so peers may push while this
+    // CTA's pipeline is still running); rows of BN * 4 bytes, 16-byte pieces XOR-swizzled by row % 8 (thread-per-row
+    // accesses would otherwise all land in the same banks)
     static constexpr uint32_t kPartOffset = kStages * kStage + 256;
     static constexpr uint32_t kPartPitch = BN * 4u;
-    static constexpr uint32_t kPartBytes = 128u * kPartPitch;
-    static constexpr int kMaxSplit = BN <= 32 ? 4 : (BN <= 64 ? 2 : 1);
-    static_assert(kSmemBytes + (kMaxSplit - 1) * kPartBytes <= 227u * 1024u, "split-K partial tiles do not fit");
+    static constexpr int kMaxSplit = BN <= 64 ? 4 : 1;
+    static constexpr uint32_t kPartMaxBytes = kMaxSplit > 1 ? 96u * kPartPitch : 0u;   // ksplit 4: 3 x 32 rows; 2: 1 x 64 rows
+    static_assert(kSmemBytes + kPartMaxBytes <= 227u * 1024u, "split-K partial tiles do not fit");
     static_assert(kStages >= 2, "pipeline needs at least two stages");
     static_assert(kAccCols <= 512, "TMEM has 512 columns");
     static_assert(kStage % 1024 == 0, "stages must stay 1024-byte aligned for SWIZZLE_128B");
@@ -127,9 +128,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     // split-K: gridDim.z CTAs of one cluster (cluster dims 1 x 1 x gridDim.z) share the output tile; CTA z walks the
-    // K chunks [it0, it0 + KC) and CTAs z > 0 hand their partial sums to CTA 0 through distributed shared memory:
-    // asynchronous remote stores (st.async) that complete transaction bytes on an mbarrier of the leader, so the
-    // hand-over costs one store latency and no cluster-wide barrier (measured: ~2.3k cycles for barrier.cluster).
+    // K chunks [it0, it0 + KC) and then finishes the TMEM lane quarters (32-row groups) it owns: the other CTAs hand
+    // it their partial sums of those rows through distributed shared memory - asynchronous remote stores (st.async)
+    // that complete transaction bytes on an mbarrier of the owner, so the hand-over needs no cluster-wide barrier
+    // (measured ~2.3k cycles) and each CTA receives only (ksplit-1)/ksplit of a tile (DSMEM moves ~20 bytes / cycle).
     const int ksplit = gridDim.z;
     const int kz = blockIdx.z;
     const int KC = ((p.K + BK - 1) / BK) / ksplit;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         mbar_init(accum_full, 1);
         mbar_init(part_full, 1);
         mbar_fence_init();
-        if (ksplit > 1 && kz == 0) mbar_arrive_expect_tx(part_full, (uint32_t)(ksplit - 1) * C::kPartBytes);
+        if (ksplit > 1) mbar_arrive_expect_tx(part_full, (uint32_t)(ksplit - 1) * (uint32_t)(BM / ksplit) * C::kPartPitch);
     }
     if (warp == 5) tmem_alloc(tmem_ptr, C::kTmemCols);
     tcgen05_fence_before();
@@ -322,7 +324,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         if (warp >= 4) pdl_wait();           // residual / add operands come from the previous kernels
         const int cbeg = half * C::kChunksW * 16;
         const int row = m0 + ew * 32 + lane;
-        const bool row_ok = row < p.M;
+        // split-K: lane quarter q is finished by CTA q * ksplit / 4; the other CTAs only contribute partial sums
+        const int owner = (ew * ksplit) >> 2;
+        const bool mine = owner == kz;
+        const bool row_ok = mine && row < p.M;
         const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
         const float* add_row = (row_ok && p.addmat) ? p.addmat + (size_t)(row % p.add_period) * p.ld_add : nullptr;
         const bool has_res = row_ok && p.res.hi != nullptr;
@@ -375,8 +380,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         };
         // v[0..15] = acc_scale * (sum over all accumulators of columns [c, c+16)); all TMEM loads of the chunk are
         // issued back to back and waited for once.
-        constexpr uint32_t kPartPitch = C::kPartPitch, kPartBytes = C::kPartBytes, kPartOffset = C::kPartOffset;
-        const uint32_t part_row = (uint32_t)(ew * 32 + lane) * kPartPitch;     // this thread's row of a partial tile
+        constexpr uint32_t kPartPitch = C::kPartPitch, kPartOffset = C::kPartOffset;
+        const uint32_t part_slot = (uint32_t)(BM / ksplit) * kPartPitch;       // one source CTA's rows in the owner's region
+        const uint32_t part_row = (uint32_t)((ew - owner * (4 / ksplit)) * 32 + lane) * kPartPitch;   // row inside a slot
         const uint32_t part_swz = (uint32_t)(lane & 7);                        // == row % 8
         // v = sum over all accumulators of columns [c, c+16), unscaled: the correction terms first (small), then the
         // main slots, RN adds; the TMEM loads of each group are issued back to back and waited for once.
@@ -413,21 +419,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 v[j] = x[j] + y;
             }
         };
-        auto load_acc = [&](int c, float (&v)[16]) {
-            sum_acc(c, v);
-            if (ksplit > 1 && kz == 0) {                  // leader: add the partial sums the peers pushed over DSMEM
+        // own sums -> final accumulator: add the peers' partial rows (split-K owner), undo the weight pre-scaling
+        auto finish_acc = [&](int c, float (&v)[16]) {
+            if (ksplit > 1) {                             // owner: add the partial sums the peers pushed over DSMEM
                 const uint8_t* part = stage_base + kPartOffset + part_row;
                 for (int peer = 0; peer < ksplit - 1; ++peer) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const uint32_t piece = ((uint32_t)((c + j) >> 2) ^ part_swz) << 4;
-                        const float4 t4 = *reinterpret_cast<const float4*>(part + (uint32_t)peer * kPartBytes + piece);
+                        const float4 t4 = *reinterpret_cast<const float4*>(part + (uint32_t)peer * part_slot + piece);
                         v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
                     }
                 }
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] *= acc_scale;
+        };
+        auto load_acc = [&](int c, float (&v)[16]) {
+            sum_acc(c, v);
+            finish_acc(c, v);
         };
 
         // Output path.  split16 row-major tiles are staged in shared memory (the pipeline stages are idle once the
@@ -496,19 +506,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         mbar_wait(accum_full, 0);
         tcgen05_fence_after();
         if (threadIdx.x == 0) COTR_TS(20);
-        if (ksplit > 1) {
-            if (kz != 0) {
-                // the partial tiles have their own region in the leader's shared memory: push as soon as this CTA's
-                // MMAs have retired, whatever the leader is doing
-                const uint32_t local = smem_u32(stage_base) + kPartOffset + (uint32_t)(kz - 1) * kPartBytes + part_row;
-                const uint32_t remote = map_to_cta(local, 0);
-                const uint32_t remote_bar = map_to_cta(smem_u32(part_full), 0);
+        // Narrow tiles read their own accumulators into registers right away: senders push them, owners overlap the
+        // TMEM round trips with the wait for the peers' partial rows.
+        constexpr bool kPreload = !LN && C::kChunksW <= 2;
+        float pre[kPreload ? C::kChunksW : 1][16];
+        if constexpr (kPreload) {
+#pragma unroll
+            for (int ci = 0; ci < C::kChunksW; ++ci) sum_acc(cbeg + ci * 16, pre[ci]);
+        }
+        if (C::kMaxSplit > 1 && ksplit > 1) {
+            if (!mine) {
+                // the partial rows have their own region in the owner's shared memory: push as soon as this CTA's
+                // MMAs have retired, whatever the owner is doing (source slot: this CTA's rank among the non-owners)
+                const uint32_t local = smem_u32(stage_base) + kPartOffset + (uint32_t)(kz < owner ? kz : kz - 1) * part_slot + part_row;
+                const uint32_t remote = map_to_cta(local, (uint32_t)owner);
+                const uint32_t remote_bar = map_to_cta(smem_u32(part_full), (uint32_t)owner);
                 // unscaled partial sums travel; the leader applies acc_scale once in load_acc
-#pragma unroll 1
+#pragma unroll
                 for (int ci = 0; ci < C::kChunksW; ++ci) {
                     const int c = cbeg + ci * 16;
-                    float v[16];
-                    sum_acc(c, v);
+                    const float (&v)[16] = pre[kPreload ? ci : 0];      // (split-K only exists on preloading tiles)
 #pragma unroll
                     for (int j = 0; j < 16; j += 4)
                         st_async_f32x4(remote + (((uint32_t)((c + j) >> 2) ^ part_swz) << 4), v[j], v[j + 1], v[j + 2], v[j + 3], remote_bar);
@@ -516,11 +533,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 if (threadIdx.x == 0) COTR_TS(22);
             } else {
                 if (threadIdx.x == 0) COTR_TS(22);
-                mbar_wait(part_full, 0);             // (ksplit - 1) x 128 rows x BN floats have landed
+                mbar_wait(part_full, 0);             // (ksplit - 1) x (128 / ksplit) rows x BN floats have landed
                 if (threadIdx.x == 0) COTR_TS(23);
             }
         }
-        if (ksplit == 1 || kz == 0) {
+        if (mine) {
 
         if constexpr (!LN) {
 #pragma unroll
@@ -528,7 +545,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 const int c = cbeg + ci * 16;
                 const int nb = n0 + c;
                 float v[16];
-                load_acc(c, v);
+                if constexpr (kPreload) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = pre[ci][j];
+                    finish_acc(c, v);
+                } else {
+                    load_acc(c, v);
+                }
                 if (threadIdx.x == 0 && ci < 2) COTR_TS(30 + 4 * ci);
                 if (BN > 16 || !tail) {                          // (a ragged N only exists in the 16-wide instantiation)
                     apply(ops[ci % C::kRing], v);
@@ -616,7 +639,7 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         COTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, LN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(C::kSmemBytes + (C::kMaxSplit - 1) * C::kPartBytes)));
+                                             (int)(C::kSmemBytes + C::kPartMaxBytes)));
         configured = true;
     }
     const int npad = tc_npad(p.N);
@@ -633,7 +656,7 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
         }
     }
     grid.z = ksplit;
-    const size_t smem = C::kSmemBytes + (size_t)(ksplit - 1) * C::kPartBytes;      // the leader's partial-tile region
+    const size_t smem = C::kSmemBytes + (size_t)(ksplit - 1) * (BM / ksplit) * C::kPartPitch;     // incoming partial rows
     COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), smem, s, ksplit, p, npad, g_tc_timestamps));
     return 0;
 }
