@@ -70,8 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
     uint64_t* o_full = bars + 3;
     uint64_t* p_full = bars + 4;     // [2]
     uint64_t* p_empty = bars + 6;    // [2]
-    uint64_t* s_full2 = bars + 8;    // second half of the score tile (keys 256..511)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -82,7 +81,6 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         mbar_init(qk_full, kSoftmaxThreads);
         mbar_init(v_full, kSoftmaxThreads);
         mbar_init(s_full, 1);
-        mbar_init(s_full2, 1);
         mbar_init(o_full, 1);
         mbar_init(&p_full[0], kSoftmaxThreads);
         mbar_init(&p_full[1], kSoftmaxThreads);
@@ -90,20 +88,13 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         mbar_init(&p_empty[1], 1);
         mbar_fence_init();
     }
-    __syncthreads();                                     // barriers are initialised
+    if (warp == 8) tmem_alloc(tmem_ptr, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
     const uint32_t sbase = smem_u32(smem);
     if (threadIdx.x == 0) COTR_TS(1);
-    // the TMEM allocation runs beside the staging copies: the MMA warp allocates and publishes the address through shared
-    // memory + named barrier 5, the softmax warps pick it up once their copies are issued
-    uint32_t tmem_base = 0;
-    if (warp == 8) {
-        tmem_alloc(tmem_ptr, 512);
-        tcgen05_fence_before();
-        fence_proxy_async_smem();
-        named_barrier_arrive(5, kThreads);
-        tcgen05_fence_after();
-        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
-    }
 
     if (warp < 8) {
         const int t = threadIdx.x;
@@ -165,9 +156,6 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
 
         // ---- softmax out of TMEM ---------------------------------------------------------------------------
         float* stat = reinterpret_cast<float*>(smem + kOffStat);         // [half][row]
-        named_barrier_sync(5, kThreads);
-        tcgen05_fence_after();
-        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
         mbar_wait(s_full, 0);
         tcgen05_fence_after();
         if (t == 0) COTR_TS(4);
@@ -175,10 +163,6 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         float mx = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < kTokens; c += 128) {
-            if (c == kTokens / 2) {                      // the row max of the first 256 keys overlaps the second S MMAs
-                mbar_wait(s_full2, 0);
-                tcgen05_fence_after();
-            }
             uint32_t r[4][16];
             __syncwarp();
 #pragma unroll
@@ -207,9 +191,9 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
             for (int h = 0; h < 2; ++h) tmem_ld16_issue(trow + c * kChunk + h * 16, r[h]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) tmem_ld16_fence(r[h]);
-            // exponentials and the hi/lo split happen in registers before the buffer is known to be free: only the
-            // stores sit behind the MMA of chunk c - 2
-            uint4 hi[4], lo[4];
+            if (c >= 2) mbar_wait(&p_empty[buf], (uint32_t)((c >> 1) - 1) & 1u);
+            uint8_t* p_hi = smem + kOffP + buf * 2 * kPPlane + (half * 4) * kPLbo + trow_i * 16;
+            uint8_t* p_lo = p_hi + kPPlane;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float v[16];
@@ -220,19 +204,14 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                 }
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    split_f16x2(v[g * 8 + 0], v[g * 8 + 1], hi[h * 2 + g].x, lo[h * 2 + g].x);
-                    split_f16x2(v[g * 8 + 2], v[g * 8 + 3], hi[h * 2 + g].y, lo[h * 2 + g].y);
-                    split_f16x2(v[g * 8 + 4], v[g * 8 + 5], hi[h * 2 + g].z, lo[h * 2 + g].z);
-                    split_f16x2(v[g * 8 + 6], v[g * 8 + 7], hi[h * 2 + g].w, lo[h * 2 + g].w);
+                    uint4 hi, lo;
+                    split_f16x2(v[g * 8 + 0], v[g * 8 + 1], hi.x, lo.x);
+                    split_f16x2(v[g * 8 + 2], v[g * 8 + 3], hi.y, lo.y);
+                    split_f16x2(v[g * 8 + 4], v[g * 8 + 5], hi.z, lo.z);
+                    split_f16x2(v[g * 8 + 6], v[g * 8 + 7], hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(p_hi + (h * 2 + g) * kPLbo) = hi;
+                    *reinterpret_cast<uint4*>(p_lo + (h * 2 + g) * kPLbo) = lo;
                 }
-            }
-            if (c >= 2) mbar_wait(&p_empty[buf], (uint32_t)((c >> 1) - 1) & 1u);
-            uint8_t* p_hi = smem + kOffP + buf * 2 * kPPlane + (half * 4) * kPLbo + trow_i * 16;
-            uint8_t* p_lo = p_hi + kPPlane;
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-                *reinterpret_cast<uint4*>(p_hi + g4 * kPLbo) = hi[g4];
-                *reinterpret_cast<uint4*>(p_lo + g4 * kPLbo) = lo[g4];
             }
             tcgen05_fence_before();
             fence_proxy_async_smem();
@@ -294,8 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                     umma_f16_ss(d, qh, kl, idesc_s, true);
                     umma_f16_ss(d, qh, kh, idesc_s, true);
                 }
-                umma_commit(nh == 0 ? s_full : s_full2);
             }
+            umma_commit(s_full);
             COTR_TS(21);
             mbar_wait(v_full, 0);
             COTR_TS(22);

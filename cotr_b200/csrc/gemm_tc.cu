@@ -148,21 +148,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         mbar_fence_init();
         if (ksplit > 1) mbar_arrive_expect_tx(part_full, (uint32_t)(ksplit - 1) * (uint32_t)(BM / ksplit) * C::kPartPitch);
     }
-    __syncthreads();                         // barriers are initialised
+    if (warp == 5) tmem_alloc(tmem_ptr, C::kTmemCols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
     // split-K: tell the cluster that this CTA runs and its barriers exist (waited for just before the first remote access)
     if (ksplit > 1) cluster_arrive();
     if (threadIdx.x == 0) COTR_TS(1);
-    // The TMEM allocation (a few hundred cycles) runs beside the first loads: the MMA warp allocates and publishes the
-    // address through shared memory + named barrier 5; the other warps pick it up when they enter the epilogue.
-    uint32_t tmem_base = 0;
-    if (warp == 5) {
-        tmem_alloc(tmem_ptr, C::kTmemCols);
-        tcgen05_fence_before();
-        fence_proxy_async_smem();
-        named_barrier_arrive(5, kThreads);
-        tcgen05_fence_after();
-        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
-    }
 
     if (warp < 4) {
         // ================= A producer ===========================================================================
@@ -327,11 +320,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = warp >> 2;              // column half of the tile it handles
     if (ksplit > 1) cluster_wait();          // every CTA of the cluster has started (long ago by now)
-    if (warp != 5) {
-        named_barrier_sync(5, kThreads);
-        tcgen05_fence_after();
-        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
-    }
     if (half < C::kEpiHalves) {
         if (warp >= 4) pdl_wait();           // residual / add operands come from the previous kernels
         const int cbeg = half * C::kChunksW * 16;
