@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(kWarps * 32) attention_simt_kernel(const AttnP
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
-    pdl_wait();
     if (tid == 0) pdl_launch_dependents();
+    pdl_wait();
     for (int idx = tid; idx < kTokens * (kHeadDim / 8); idx += blockDim.x) {        // K rows: 8 elements per step
         const int key = idx >> 2, d8 = (idx & 3) * 8;
         float v[8];

@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         const bool row_ok = qi < p.nq;
         const size_t grow = (size_t)pair_local * p.nq + (row_ok ? qi : 0);
         const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
+        if (t == 0) pdl_launch_dependents();             // the next kernel may start its prologue on idle SMs
         pdl_wait();                                      // prologue above overlaps the previous kernel
-        if (t == 0) pdl_launch_dependents();
         if (t == 0) COTR_TS(2);
 
         // ---- stage Q (row t % 128, two of the four 16-byte K groups per thread) and K (4 keys per thread) --------

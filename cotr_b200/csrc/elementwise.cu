@@ -10,8 +10,8 @@ namespace {
 __global__ void maxpool_3x3s2_nhwc_kernel(const CSplit16 in, const Split16 out, int N, int H, int W, int C8) {
     const int OH = H / 2, OW = W / 2;
     const size_t total = (size_t)N * OH * OW * C8;
-    pdl_wait();
     if (threadIdx.x == 0) pdl_launch_dependents();
+    pdl_wait();
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         const int c8 = idx % C8;
@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(256) layernorm256_kernel(const CSplit16 x, con
                                                            const Split16 out, int rows) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    pdl_wait();
     if (threadIdx.x == 0) pdl_launch_dependents();
+    pdl_wait();
     if (warp >= rows) return;
     const size_t off = (size_t)warp * kDModel + lane * 8;
     float v[8];
@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(256) layernorm256_kernel(const CSplit16 x, con
 // channel 2(k-1)+a = sin(fp32(k*pi) * p_a), channel 128 + 2(k-1)+a = cos(...).  Accurate sincosf: |angle| <= 64*pi.
 __global__ void __launch_bounds__(128) query_encode_kernel(const float* __restrict__ queries, const Split16 qpos, int rows) {
     const int row = blockIdx.x;
-    pdl_wait();
     if (threadIdx.x == 0) pdl_launch_dependents();
+    pdl_wait();
     if (row >= rows) return;
     const int t = threadIdx.x;          // 0..127 = 2*(k-1) + axis
     const int k = (t >> 1) + 1;

@@ -29,8 +29,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p, floa
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
-    pdl_wait();
     if (tid == 0) pdl_launch_dependents();
+    pdl_wait();
 
     const int lrow = tid >> 2;          // 0..63
     const int lk = (tid & 3) * 4;       // 0,4,8,12

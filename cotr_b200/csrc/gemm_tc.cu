@@ -168,8 +168,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         const uint32_t a_off = (uint32_t)rb * 128u + (uint32_t)((kg ^ (rb & 7)) << 4);   // swizzled chunk position
         const uint32_t dst0 = smem_u32(stage_base) + a_off;
         // everything above (and the weight TMA of warp 4) overlaps the previous kernel; activations do not
-        pdl_wait();
+        // Let the next kernel of the stream / graph start its prologue (barriers, TMEM, weight TMA) on idle SMs now; it
+        // still waits (griddepcontrol.wait) for this grid to complete before touching activations.  (Same-box A/B:
+        // triggering here beats triggering after the wait by 0.5%, triggering at kernel entry loses 1.4%.)
         if (threadIdx.x == 0) pdl_launch_dependents();
+        pdl_wait();
         if (threadIdx.x == 0) COTR_TS(2);
 
 #pragma unroll 1
@@ -650,7 +653,7 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     if constexpr (!LN && BN <= 64 && MODE != LD_STEM) {
         const int kc = (p.K + BK - 1) / BK;
         const long long ctas = (long long)grid.x * grid.y;
-        if (!(g_tc_variant & 512) && kc >= ((g_tc_variant & 16384) ? 8 : 16)) {
+        if (!(g_tc_variant & 512) && kc >= (16 >> ((g_tc_variant >> 14) & 3))) {     // bring-up knob: bits 14-15
             if (C::kMaxSplit >= 4 && kc % 4 == 0 && ctas * 4 <= 160) ksplit = 4;
             else if (C::kMaxSplit >= 2 && kc % 2 == 0 && ctas * 2 <= 160) ksplit = 2;
         }

@@ -324,6 +324,9 @@ def timing():
 
 
 def run_stage(name):
+    if os.environ.get("COTR_B200_LIB"):          # dev: run a stage against another build (tools/ab_libs.py)
+        from cotr_b200 import capi
+        capi.LIB_PATH = os.environ["COTR_B200_LIB"]
     if name == "gemm_simt":
         gemm_cases(1)
     elif name == "attn_simt":
