@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, 512);
     if (threadIdx.x == 0) COTR_TS(60);
+    if (my_ts && threadIdx.x == 0) my_ts[62] = global_ns();
 #undef COTR_TS
 }
 
@@ -328,7 +329,7 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
     COTR_CHECK((p.ldq & 7) == 0 && (p.ldk & 7) == 0 && (p.ldo & 7) == 0 && (p.vt_pair_stride & 7) == 0,
                "attention_tc: leading dimensions must be multiples of 8 elements");
     dim3 grid((p.nq + kTile - 1) / kTile, kHeads, p.npairs);
-    COTR_CHECK_CUDA(launch_kernel(attention_tc_kernel, grid, dim3(kThreads), kSmemBytes, s, p, g_tc_timestamps));
+    COTR_CHECK_CUDA(launch_kernel(attention_tc_kernel, grid, dim3(kThreads), kSmemBytes, s, p, next_trace_block()));
     return 0;
 }
 

@@ -35,7 +35,21 @@ void set_error(const char* fmt, ...);
 // ---------------------------------------------------------------------------------------------------------------
 extern int g_use_pdl;
 extern long long* g_tc_timestamps;   // debug timeline buffer of the tcgen05 kernels (cotr_debug_set_timestamps), else null
+extern int g_tc_variant;
+extern int g_tc_trace_idx;
+// Trace mode (cotr_debug_set_variant bit 17 + a timestamp buffer): every tcgen05 launch gets its own block of
+// 256 CTAs x 64 slots, so one forward (graph replay included) leaves a per-launch record; slots 61-63 hold %globaltimer.
+inline long long* next_trace_block() {
+    if (!g_tc_timestamps) return nullptr;
+    if (!(g_tc_variant & (1 << 17))) return g_tc_timestamps;
+    return g_tc_timestamps + (size_t)(g_tc_trace_idx++) * 64 * 256;
+}
 #ifdef __CUDACC__
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif

@@ -39,6 +39,7 @@ namespace cotr {
 int g_tc_variant = 0;                   // bring-up switch (reserved)
 int g_use_pdl = 1;                      // programmatic dependent launch (common.cuh); cotr_debug_set_variant bit 8 clears it
 long long* g_tc_timestamps = nullptr;   // debug: 64 clock64() stamps per CTA (cotr_debug_set_timestamps), else null
+int g_tc_trace_idx = 0;                 // trace mode: launch counter (common.cuh next_trace_block)
 
 namespace {
 
@@ -633,6 +634,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, C::kTmemCols);
     if (threadIdx.x == 160) COTR_TS(60);
+    if (my_ts && threadIdx.x == 160) my_ts[62] = global_ns();
 #undef COTR_TS
 }
 
@@ -660,7 +662,7 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     }
     grid.z = ksplit;
     const size_t smem = C::kSmemBytes + (size_t)(ksplit - 1) * (BM / ksplit) * C::kPartPitch;     // incoming partial rows
-    COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), smem, s, ksplit, p, npad, g_tc_timestamps));
+    COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), smem, s, ksplit, p, npad, next_trace_block()));
     return 0;
 }
 

@@ -874,7 +874,7 @@ int forward_eager(cotr_model* m, const float* img, const float* queries, int B, 
 // Forward on the staging buffers (img_stage, q_stage -> pred_stage): graph replay when a graph exists for the shape.
 int forward_staged(cotr_model* m, int B, int Q, cudaStream_t s) {
     Workspace& w = m->ws;
-    const bool graphable = m->graph_mode && !m->prof_on && g_tc_timestamps == nullptr;
+    const bool graphable = m->graph_mode && !m->prof_on && (g_tc_timestamps == nullptr || (g_tc_variant & (1 << 17)));
     const long long key = ((long long)B << 32) | (unsigned)Q;
     if (graphable) {
         auto it = m->graphs.find(key);
@@ -918,7 +918,7 @@ int cotr_forward(cotr_model* m, const float* img_dev, const float* queries_dev, 
     COTR_CHECK(B >= 1 && Q >= 0, "cotr_forward: B must be >= 1 and Q >= 0");
     COTR_CHECK_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    const bool graphable = m->graph_mode && !m->prof_on && g_tc_timestamps == nullptr && Q > 0;
+    const bool graphable = m->graph_mode && !m->prof_on && (g_tc_timestamps == nullptr || (g_tc_variant & (1 << 17))) && Q > 0;
     if (!graphable) return forward_eager(m, img_dev, queries_dev, B, Q, pred_dev, s);
     // graph replay needs fixed addresses: go through the staging buffers (two small device-to-device copies in, one out)
     if (ensure_stage(m, B, Q)) return 1;
@@ -1039,7 +1039,10 @@ int cotr_set_gemm_path(cotr_model* m, int path) {
 }
 
 void cotr_debug_set_variant(int variant) { g_tc_variant = variant; g_use_pdl = (variant & 256) ? 0 : 1; }
-void cotr_debug_set_timestamps(void* dev_buffer) { g_tc_timestamps = reinterpret_cast<long long*>(dev_buffer); }
+void cotr_debug_set_timestamps(void* dev_buffer) {
+    g_tc_timestamps = reinterpret_cast<long long*>(dev_buffer);
+    g_tc_trace_idx = 0;
+}
 
 // ---- kernel-level test hooks: fp32 device tensors in / out, converted to split16 around the kernel under test -------
 namespace {

@@ -216,6 +216,63 @@ def attn_timeline():
                   f" | O ready {r[14]} stored {r[15]} end {r[60]}", flush=True)
 
 
+def forward_trace():
+    """%globaltimer trace of one graph-replayed forward (B=1, Q=1024): per tcgen05 launch, CTA 0's kernel entry, the
+    return of griddepcontrol.wait and the CTA exit, in microseconds since the first launch (variant bit 17)."""
+    import ctypes
+    import torch
+    from cotr_b200 import capi
+    from cotr_b200.models import build_model
+    from oracle import fixtures
+    sd = fixtures.make_state_dict(0)
+    model = build_model(None)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.cuda().eval()
+    img, q = fixtures.make_inputs(1, 1, 1024)
+    img = torch.from_numpy(img).cuda(); q = torch.from_numpy(q).cuda()
+    n_launch = int(os.environ.get("COTR_TRACE_N", "112"))
+    ts = torch.zeros(n_launch * 256 * 64, dtype=torch.int64, device="cuda")
+    capi.lib().cotr_debug_set_variant(1 << 17)
+    for rep in range(4):                      # eager, capture, replay, replay
+        capi.lib().cotr_debug_set_timestamps(ctypes.c_void_p(ts.data_ptr()))
+        model(img, q)
+        torch.cuda.synchronize()
+    capi.lib().cotr_debug_set_timestamps(None)
+    capi.lib().cotr_debug_set_variant(0)
+    t = ts.cpu().view(n_launch, 256, 64)
+    t0 = None
+    prev_end = None
+    rows = []
+    for i in range(n_launch):
+        ctas = t[i]
+        # %globaltimer is read once per CTA, at exit (slot 62), next to the exit cycle stamp (slot 60): a second read
+        # shortly after a first one stalls the reading thread for microseconds (measured), so entry and wait-done times
+        # are reconstructed from the SM cycle counter
+        ctas = ctas.clone()
+        ctas[:, 61] = torch.where(ctas[:, 62] > 0, ctas[:, 62] - (ctas[:, 60].double() / 1.965).long(), ctas[:, 61])
+        used = ctas[:, 62] > 0
+        if not used.any():
+            continue
+        # the wait-done time comes from CTA 0's cycle counter: a second %globaltimer read shortly after the first
+        # stalls the reading thread for several microseconds (measured), so kernels read it at entry and exit only
+        start = ctas[used, 61].min().item(); first = ctas[0, 61].item(); waited = first + int(ctas[0, 2].item() / 1.965)
+        end = ctas[used, 62].max().item(); end0 = ctas[0, 62].item()
+        if t0 is None:
+            t0 = start
+        rows.append((i, int(used.sum()), (start - t0) / 1e3, (waited - t0) / 1e3, (end0 - t0) / 1e3, (end - t0) / 1e3))
+    for i in [int(x) for x in os.environ.get("COTR_TRACE_DETAIL", "").split(",") if x]:
+        ctas = t[i].clone()
+        ctas[:, 61] = torch.where(ctas[:, 62] > 0, ctas[:, 62] - (ctas[:, 60].double() / 1.965).long(), ctas[:, 61])
+        for c in range(256):
+            if ctas[c, 61] > 0 and (c < 6 or c % 16 == 0):
+                print(f"    launch {i} cta {c:3d}: start {(ctas[c, 61].item() - t0) / 1e3:8.2f} wait done {(ctas[c, 61].item() + ctas[c, 2].item() / 1.965 - t0) / 1e3:8.2f} "
+                      f"end {(ctas[c, 62].item() - t0) / 1e3:8.2f}   cycles: setup {ctas[c, 1].item()} wait {ctas[c, 2].item()} end {ctas[c, 60].item()}", flush=True)
+    for (i, n, start, waited, end0, end) in rows:
+        gap = "" if prev_end is None else f" gap after prev end {start - prev_end:+6.2f}"
+        print(f"  launch {i:3d} ctas {n:3d}: first CTA start {start:8.2f}  cta0 wait done {waited:8.2f}  cta0 end {end0:8.2f}  last CTA end {end:8.2f} us{gap}", flush=True)
+        prev_end = end
+
+
 def launch_profile():
     """Per-launch CUDA-event durations of one eager forward (B=1, Q=1024), library profiler."""
     import torch
@@ -347,6 +404,8 @@ def run_stage(name):
         launch_profile()
     elif name == "gemm_timeline":
         gemm_timeline()
+    elif name == "forward_trace":
+        forward_trace()
     elif name == "attn_timeline":
         attn_timeline()
     elif name == "backbone_timeline":
