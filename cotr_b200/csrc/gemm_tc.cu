@@ -2,12 +2,13 @@
 //
 // Precision: the 1e-3 parity bar on predicted (x,y) rules out single-pass bf16 / tf32 / fp16 operands
 // (SURVEY.md appendix E.3).  Every operand is a pair of fp16 values (x ~= hi + lo, ~22 mantissa bits) and a product
-// is formed as  hi*hi + hi*lo + lo*hi  with fp32 accumulation in TMEM - three kind::f16 MMAs per K step.  Weights are
-// pre-multiplied by a per-tensor power of two so that their lo terms stay in fp16's normal range; the epilogue
-// multiplies the accumulator by the inverse (exact).  The tensor core adds into its fp32 accumulator with truncation
-// (measured: ~1e-7 relative per chained MMA, profiles/r01_tc_precision.md), so the K steps are dealt round-robin onto
-// several TMEM accumulators and the small hi*lo / lo*hi products onto a separate one; the epilogue adds them up with
-// fp32 round-to-nearest.
+// is formed as  hi*hi + hi*lo + lo*hi  with fp32 accumulation in TMEM - three kind::f16 MMAs per K step on wide tiles,
+// two on narrow ones (the hi and lo weight planes are adjacent in the stage, so one MMA of N = 2 BN computes
+// A_hi * [B_hi; B_lo]; see Cfg::kStacked).  Weights are pre-multiplied by a per-tensor power of two so that their lo
+// terms stay in fp16's normal range; the epilogue multiplies the accumulator by the inverse (exact).  The tensor core
+// adds into its fp32 accumulator with truncation (measured: ~1e-7 relative per chained MMA,
+// profiles/r01_tc_precision.md), so the K steps are dealt round-robin onto several TMEM accumulators and the small
+// hi*lo / lo*hi products onto separate columns; the epilogue adds them up with fp32 round-to-nearest.
 //
 // Data movement per CTA (one 128 x BN output tile, K walked in chunks of 64).  Both operands sit in shared memory in
 // the SWIZZLE_128B K-major layout (128-byte rows, 16-byte chunks XOR-swizzled by row % 8):
@@ -18,7 +19,9 @@
 //     128-byte row on both sides: coalesced reads, conflict-free writes) whose completion arrives on the stage's
 //     mbarrier (cp.async.mbarrier.arrive.noinc) - no registers, no conversion, up to kStages chunks in flight.  Only
 //     the 7x7 stem reads the caller's fp32 canvas and converts in registers;
-//   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma (N = BN) and owns TMEM;
+//   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma and owns TMEM;
+//   * long reductions on under-filled grids are split over a thread-block cluster (1 x 1 x {2,4}) and reduce-scattered
+//     over TMEM lane quarters through distributed shared memory (st.async + mbarrier, no cluster barrier);
 //   * all 8 warps then run the epilogue out of TMEM (the epilogue is instruction-issue bound, so it gets two warps per
 //     scheduler: warp w owns TMEM lanes 32 (w % 4).. and the column half w / 4 of the tile; software pipelined: the
 //     global operands of chunk c+1 are in flight while chunk c is combined): bias / constant add-matrix / residual /
