@@ -270,7 +270,12 @@ def run_native(args, rank, local_rank, world):
     step_tf = algorithmic_flop(1, N_QUERIES) / (dev_ms * 1e-3) / 1e12
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": achieved_tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+        "frac": achieved_tf / peaks["bf16_tflops"],
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four gemm_tc launches of the committed
+        # `ncu --set full` capture (profiles/r01_final_ncu_summary.md: 2.93 / 1.36 / 1.63 / 3.72 MB read, 0 written;
+        # algorithmic bytes of the same launches 2.8 / 1.3 / 1.6 / 3.4 MB)
+        "traffic": 2.41e6 if dom == "gemm_tc" else None, "traffic_unit": "bytes per launch (ncu capture, not measured live)",
+        "peak_source": peaks["source"],
         "launches_per_step": d["launches"] // args.steps, "kernel_ms_per_step": d["ms"] / args.steps,
         "kernel_share_of_step": d["ms"] / sum(v["ms"] for v in per_kernel.values()),
         "whole_step": {"algorithmic_gflop": algorithmic_flop(1, N_QUERIES) / 1e9, "achieved": step_tf, "frac": step_tf / peaks["bf16_tflops"]},
