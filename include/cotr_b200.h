@@ -141,10 +141,16 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
 /* out[(p*nq+i), h*32+d] = softmax(q k^T) v per head; q (npairs*nq,256), k/v (npairs*512,256), all DEVICE, ld 256. */
 int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const float* v_dev, float* out_dev,
                         int nq, int npairs);
-/* bring-up switch: bit 8 (256) disables programmatic dependent launch. */
+/* bring-up / A-B switches (0 = production): bit 8 (256) disables programmatic dependent launch, bit 9 (512) disables
+ * split-K, bits 10-11 / 12-13 move the CTA-count thresholds of the 64- / 128-wide GEMM tiles, bits 14-15 lower the
+ * minimum K of split-K (16 >> n chunks of 64), bit 17 selects trace mode for cotr_debug_set_timestamps.
+ * Process-wide; graphs captured under another value are NOT dropped (call cotr_set_gemm_path twice to drop them). */
 void cotr_debug_set_variant(int variant);
-/* debug timeline of the tcgen05 GEMM: DEVICE buffer of 64 int64 per CTA receiving clock64() deltas of the pipeline
- * events of every following GEMM launch (NULL switches it off).  Slot layout: tools/bringup.py::gemm_timeline. */
+/* debug timeline of the tcgen05 kernels: DEVICE buffer of 64 int64 per CTA receiving clock64() deltas of the pipeline
+ * events of every following GEMM / attention launch (NULL switches it off; graph replay is off while it is set).
+ * Slot layout: tools/bringup.py::gemm_timeline / attn_timeline.  Trace mode (variant bit 17): the buffer holds
+ * 256 x 64 slots PER LAUNCH (launch counter reset by this call), slot 62 receives %globaltimer at CTA exit, and graph
+ * replay stays on - tools/bringup.py::forward_trace reconstructs a per-launch schedule of one forward from it. */
 void cotr_debug_set_timestamps(void* dev_buffer);
 
 const char* cotr_last_error(void);
