@@ -275,11 +275,18 @@ class SparseEngine():
 
 
 class FasterSparseEngine(SparseEngine):
-    """Nearby tasks share one network context: faster, slightly less accurate (:267-427)."""
+    """Nearby tasks share one network context: faster, slightly less accurate (:267-427).
 
-    def __init__(self, model, batch_size, mode='stretching', max_load=256, device_preprocess=True):
+    `rescue_stranded` (default False = the reference's behaviour) finishes, one query per context, the tasks the
+    reference silently drops: a zoom level stops grouping as soon as one invocation solves <= batch_size sub-tasks
+    (:398-399), and the single-query fallback only picks up tasks sitting at the LAST zoom value (:401-411), so tasks
+    left behind at an earlier level never reach 'finished' (SURVEY.md section 3.3).
+    """
+
+    def __init__(self, model, batch_size, mode='stretching', max_load=256, device_preprocess=True, rescue_stranded=False):
         super().__init__(model, batch_size, mode=mode, device_preprocess=device_preprocess)
         self.max_load = max_load
+        self.rescue_stranded = rescue_stranded
         self._squad_pixels_on_device = False
 
     def infer_batch_grouped(self, img_batch, query_batch):
@@ -380,4 +387,6 @@ class FasterSparseEngine(SparseEngine):
                     break
         # one-query-per-context fallback, only for tasks sitting at the LAST zoom value (:401-411)
         self._single_query_loop(tasks, max_corrs, zm)
+        if self.rescue_stranded:
+            self._single_query_loop(tasks, max_corrs)     # whatever is still open, at whatever level it was left
         return self._finish(tasks, max_corrs, return_idx, force, return_tasks_only, img_a.shape[:2], img_b.shape[:2])

@@ -40,6 +40,26 @@ def test_faster_engine_strands_ungrouped_tasks(golden_dir):
     assert gold["out0"].shape[0] < 40
 
 
+def test_rescue_stranded_flag_finishes_every_task(capsys):
+    """Opt-in fix of that quirk: with rescue_stranded=True every forced query comes back, and the tasks the grouped
+    phase did finish are answered exactly as without the flag (the extra work only touches the stranded ones)."""
+    from oracle.fake_model import FakeCOTR, synthetic_image
+    img_a = synthetic_image(1, 300, 400)
+    img_b = synthetic_image(2, 360, 288)
+    q = np.random.RandomState(5).uniform([5, 5], [395, 295], size=(40, 2))
+    zooms = np.linspace(0.5, 0.0625, 4)
+    out = {}
+    for flag in (False, True):
+        fix_randomness(0)
+        eng = FasterSparseEngine(FakeCOTR(), 4, mode='tile', max_load=16, rescue_stranded=flag)
+        out[flag] = eng.cotr_corr_multiscale(img_a, img_b, zooms, 1, max_corrs=40, queries_a=q.copy(), force=True, return_idx=True)
+    (corr0, idx0), (corr1, idx1) = out[False], out[True]
+    assert len(idx0) < 40 and len(idx1) == 40 and sorted(idx1.tolist()) == list(range(40))
+    pos = {int(i): k for k, i in enumerate(idx1)}
+    for k, i in enumerate(idx0):
+        np.testing.assert_array_equal(corr0[k], corr1[pos[int(i)]])
+
+
 def test_patch_geometry_edge_cases():
     img_shape = (300, 400, 3)
     # clamped at the top-left: shifted, not shrunk (inference_helper.py:88-98)
