@@ -44,6 +44,7 @@ _PROTOTYPES = {
     "cotr_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "cotr_preprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_dense_postprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_set_graph_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cotr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "cotr_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -176,6 +177,14 @@ class NativeModel:
                                     _ptr(img_to_dev), img_to_dev.shape[0], img_to_dev.shape[1],
                                     ctypes.c_void_p(rects.ctypes.data), n, _ptr(canvas), self._stream()), "cotr_preprocess")
         return canvas
+
+    def dense_postprocess(self, pred_dev):
+        """(n, 131072, 2) fp32 predictions of the dense grid queries -> (n, 256, 512, 3) [x, y, confidence] (device)."""
+        pred_dev = pred_dev.contiguous()
+        n = pred_dev.shape[0]
+        out = torch.empty((n, 256, 512, 3), dtype=torch.float32, device=pred_dev.device)
+        check(lib().cotr_dense_postprocess(self.handle, _ptr(pred_dev), n, _ptr(out), self._stream()), "cotr_dense_postprocess")
+        return out
 
     def set_graph_mode(self, enabled):
         check(lib().cotr_set_graph_mode(self.handle, int(bool(enabled))), "cotr_set_graph_mode")

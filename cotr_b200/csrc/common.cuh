@@ -194,6 +194,9 @@ int launch_query_encode(const float* queries, Split16 qpos, int rows, cudaStream
 int launch_f32_to_split16(const float* in, Split16 out, size_t n, cudaStream_t s);
 int launch_split16_to_f32(CSplit16 in, float* out, size_t n, cudaStream_t s);
 
+// Device-side post-processing of the dense pass (dense_post.cu)
+int dense_post_launch(const float* pred, float* out, int n, cudaStream_t s);
+
 // Device-side crop + Pillow-exact resize + normalise (preprocess.cu)
 struct Preprocessor;
 Preprocessor* preprocessor_create();

@@ -958,6 +958,12 @@ int cotr_preprocess(cotr_model* m, const uint8_t* img_from_dev, int h_from, int 
                              (cudaStream_t)cuda_stream);
 }
 
+int cotr_dense_postprocess(cotr_model* m, const float* pred_dev, int n, float* out_dev, void* cuda_stream) {
+    COTR_CHECK(m != nullptr, "cotr_dense_postprocess: null model");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    return dense_post_launch(pred_dev, out_dev, n, (cudaStream_t)cuda_stream);
+}
+
 int cotr_set_graph_mode(cotr_model* m, int enabled) {
     COTR_CHECK(m != nullptr, "cotr_set_graph_mode: null model");
     m->graph_mode = enabled != 0;

@@ -20,6 +20,7 @@ from ..utils.utils import ImagePatch
 THRESHOLD_SPARSE = 0.02
 THRESHOLD_PIXELS_RELATIVE = 0.02
 BASE_ZOOM = 1.0
+DEVICE_DENSE_POST = True   # native model: finish the dense pass on the device (cotr_dense_postprocess); False = host path
 THRESHOLD_AREA = 0.02
 LARGE_GPU = True
 
@@ -126,10 +127,14 @@ def _dense_pass(model, img_a, img_b):
     if LARGE_GPU:
         try:
             queries = torch.from_numpy(grid.reshape(-1, 2))[None].float().to(device)
-            out = model.forward(img, queries)['pred_corrs'].detach().cpu().numpy()[0]
-            out = out.reshape(MAX_SIZE, MAX_SIZE * 2, -1)
+            pred = model.forward(img, queries)['pred_corrs'].detach()
         except Exception:
             assert 0, 'set LARGE_GPU to False'
+        if DEVICE_DENSE_POST and pred.is_cuda and hasattr(model, 'dense_postprocess'):
+            # the native model finishes the pass on the device (cycle grid_sample, confidence, per-half x remap)
+            corr = model.dense_postprocess(pred).cpu().numpy()[0]
+            return corr[:, :MAX_SIZE, :], corr[:, MAX_SIZE:, :]
+        out = pred.cpu().numpy()[0].reshape(MAX_SIZE, MAX_SIZE * 2, -1)
     else:
         if hasattr(model, 'encode_context'):
             ctx = model.encode_context(img)

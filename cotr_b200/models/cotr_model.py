@@ -240,6 +240,13 @@ class COTR(nn.Module):
         return self.native().preprocess(img_from_u8.contiguous(), img_to_u8.contiguous(), rects)
 
     @torch.no_grad()
+    def dense_postprocess(self, pred):
+        """Device-side tail of the dense pass (inference_helper.py:131-145): (n,131072,2) predictions of the canvas grid
+        queries -> (n,256,512,3) [x in the other image, y, cycle confidence] (cotr_dense_postprocess)."""
+        assert pred.dtype == torch.float32 and pred.ndim == 3 and pred.shape[1] == 256 * 512 and pred.shape[2] == 2
+        return self.native().dense_postprocess(pred)
+
+    @torch.no_grad()
     def encode_context(self, samples):
         x = self._canvas(samples)
         nat = self.native()

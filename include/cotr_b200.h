@@ -88,6 +88,13 @@ int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries
 int cotr_preprocess(cotr_model* m, const uint8_t* img_from_dev, int h_from, int w_from, const uint8_t* img_to_dev, int h_to,
                     int w_to, const int32_t* rects_host, int n, float* canvas_dev, void* cuda_stream);
 
+/* Device-side post-processing of the dense first guess (COTR/inference/inference_helper.py:131-145, the host work of
+ * cotr_patch_flow_exhaustive after the 131 072-query forward): pred_dev holds n x (256*512) x 2 fp32 predictions for the
+ * grid queries (j/512, i/256) in row-major (i, j) order; out_dev receives n x 256 x 512 x 3 fp32
+ * [x in the other image's [-1,1] frame, y in [-1,1], cycle-consistency confidence] exactly as the reference's
+ * `corr` array before it is split into its two halves (grid_sample: bilinear, zero padding, align_corners = False). */
+int cotr_dense_postprocess(cotr_model* m, const float* pred_dev, int n, float* out_dev, void* cuda_stream);
+
 /* cotr_forward / cotr_forward_host replay a CUDA graph per (B,Q) shape (captured on the second call with that shape;
  * inputs / outputs pass through internal staging buffers so the graph's addresses stay fixed).  0 disables it. */
 int cotr_set_graph_mode(cotr_model* m, int enabled);

@@ -48,6 +48,41 @@ def test_dense_flow_matches_oracle(models):
         assert np.abs(g - r).max() < 4e-3, name
 
 
+def test_device_dense_postprocess_matches_host_path(models):
+    """cotr_dense_postprocess against the reference's host tail of the dense pass (inference_helper.py:131-145: torch
+    grid_sample on the CPU, norm, per-half remap) on the same predictions.  fp32 both sides; the tolerance covers the
+    different summation order of the four bilinear taps (2e-6 on values in [-3, 3])."""
+    from cotr_b200.inference import inference_helper as ih
+    native, _ = models
+    img_a = synthetic_image(37, 256, 256)
+    img_b = synthetic_image(38, 256, 256)
+    out = {}
+    for flag in (True, False):
+        ih.DEVICE_DENSE_POST = flag
+        try:
+            out[flag] = ih._dense_pass(native, img_a, img_b)
+        finally:
+            ih.DEVICE_DENSE_POST = True
+    for dev, host in zip(out[True], out[False]):
+        assert dev.shape == host.shape == (256, 256, 3) and dev.dtype == host.dtype == np.float32
+        assert np.isfinite(dev).all()
+        assert np.abs(dev - host).max() < 2e-6, np.abs(dev - host).max(axis=(0, 1))
+    # synthetic predictions that leave the canvas exercise the zero padding of grid_sample
+    rs = np.random.RandomState(11)
+    pred = torch.from_numpy(rs.uniform(-0.3, 1.3, size=(2, 256 * 512, 2)).astype(np.float32)).cuda()
+    dev = native.dense_postprocess(pred).cpu()
+    for n in range(2):
+        og = pred[n].cpu().view(1, 256, 512, 2) * 2 - 1
+        cyc = torch.nn.functional.grid_sample(og.permute(0, 3, 1, 2), og, align_corners=False).permute(0, 2, 3, 1)[0]
+        grid = torch.from_numpy(ih._dense_grid()).float() * 2 - 1
+        conf = torch.norm(cyc - grid, dim=-1)
+        ref = og[0].clone()
+        ref[:, :256, 0] = ref[:, :256, 0] * 2 - 1
+        ref[:, 256:, 0] = ref[:, 256:, 0] * 2 + 1
+        ref = torch.cat([ref, conf[..., None]], dim=-1)
+        assert (dev[n] - ref).abs().max().item() < 4e-6
+
+
 def test_sparse_engine_matches_oracle_in_pixels(models, capsys):
     from cotr_b200.inference.sparse_engine import SparseEngine
     from cotr_b200.utils.utils import fix_randomness
