@@ -99,10 +99,9 @@ constexpr size_t kSmemBytes = (size_t)(kTokens * kKStride + kTokens * kHeadDim +
 
 int launch_attention_simt(const AttnParams& p, cudaStream_t s) {
     if (p.nq <= 0 || p.npairs <= 0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;      // bit per device
+    if (first_use_on_device(&configured)) {
         COTR_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        configured = true;
     }
     COTR_CHECK(p.npairs <= 65535, "attention: too many pairs in one launch (%d)", p.npairs);
     dim3 grid((p.nq + kRowsPerCta - 1) / kRowsPerCta, kHeads, p.npairs);

@@ -320,10 +320,9 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
 int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
     if (p.nq <= 0 || p.npairs <= 0) return 0;
     if (p.nq < 32) return launch_attention_simt(p, s);   // a 128-row MMA tile would be > 75% padding
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;      // bit per device
+    if (first_use_on_device(&configured)) {
         COTR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        configured = true;
     }
     COTR_CHECK(p.npairs <= 65535, "attention: too many pairs in one launch (%d)", p.npairs);
     COTR_CHECK((p.ldq & 7) == 0 && (p.ldk & 7) == 0 && (p.ldo & 7) == 0 && (p.vt_pair_stride & 7) == 0,

@@ -54,6 +54,17 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
+// Function attributes (opt-in dynamic shared memory) are per device, and one process may hold one handle per device:
+// remember per kernel on which devices it has been configured.  (Racing first uses merely set the attribute twice.)
+inline bool first_use_on_device(unsigned long long* configured_mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*configured_mask & bit) return false;
+    *configured_mask |= bit;
+    return true;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};

@@ -644,11 +644,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 template <int BN, bool LN, int MODE>
 int launch_one(const GemmParams& p, cudaStream_t s) {
     using C = Cfg<BN>;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;      // bit per device
+    if (first_use_on_device(&configured)) {
         COTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, LN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(C::kSmemBytes + C::kPartMaxBytes)));
-        configured = true;
     }
     const int npad = tc_npad(p.N);
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
