@@ -57,7 +57,8 @@ def one(path):
     model = model.cuda().eval()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     out = []
-    for (B, Q, n) in ((1, 1024, 60), (8, 1024, 12), (1, 16384, 12)):
+    shapes = ((1, 1024, 60),) if os.environ.get("COTR_AB_QUICK") else ((1, 1024, 60), (8, 1024, 12), (1, 16384, 12))
+    for (B, Q, n) in shapes:
         img, q = fixtures.make_inputs(1, B, Q)
         img = torch.from_numpy(img).cuda(); q = torch.from_numpy(q).cuda()
         for _ in range(5):
@@ -74,7 +75,7 @@ def one(path):
     print(" | ".join(out), flush=True)
 
 
-def run(names, rounds=3):
+def run(names, rounds=int(os.environ.get("COTR_AB_ROUNDS", "3"))):
     for r in range(rounds):
         for name in names:
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "one", lib_path(name)], capture_output=True, text=True)
