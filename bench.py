@@ -174,7 +174,7 @@ def run_native(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from cotr_b200.models import build_model
-    from oracle import fixtures   # seeded synthetic weights / inputs only (no oracle compute on this path)
+    from cotr_b200.utils import synthetic as fixtures   # seeded synthetic weights / inputs (nothing under oracle/ on this path)
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -288,7 +288,7 @@ def run_native(args, rank, local_rank, world):
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (fp16 hi/lo split operands, fp32 accumulate on tcgen05)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": 1, "queries_per_pair": N_QUERIES, "parallelism": f"dp{world} (independent pairs)",
-                   "l2": "flushed between timed steps by writing a 256 MiB buffer", "weights": "seeded synthetic (oracle/fixtures.py seed 0)",
+                   "l2": "flushed between timed steps by writing a 256 MiB buffer", "weights": "seeded synthetic (cotr_b200/utils/synthetic.py seed 0)",
                    "result_gather": "nccl all_gather inside the step" if world > 1 else "none (single GPU)"},
         "e2e": {"value": total_q / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(img_np.nbytes + q_np.nbytes), "d2h_bytes_per_step": int(out_pin.numel() * 4),

@@ -34,11 +34,4 @@ class FakeCOTR(nn.Module):
         return {'pred_corrs': pred}
 
 
-def synthetic_image(seed, h, w):
-    """Smooth seeded uint8 RGB texture (low-frequency random field + gradient)."""
-    rs = np.random.RandomState(seed)
-    import cv2
-    small = rs.uniform(0, 255, (h // 16 + 2, w // 16 + 2, 3)).astype(np.float32)
-    img = cv2.resize(small, (w, h), interpolation=cv2.INTER_CUBIC)
-    img += np.linspace(-30, 30, w, dtype=np.float32)[None, :, None]
-    return np.clip(img, 0, 255).astype(np.uint8)
+from cotr_b200.utils.synthetic import synthetic_image  # noqa: E402,F401  (kept under its old name for the tests)

@@ -50,7 +50,7 @@ def one(path):
     from cotr_b200 import capi
     capi.LIB_PATH = path
     from cotr_b200.models import build_model
-    from oracle import fixtures
+    from cotr_b200.utils import synthetic as fixtures
     sd = fixtures.make_state_dict(0)
     model = build_model(None)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})

@@ -9,7 +9,7 @@ sys.path.insert(0, REPO)
 import torch
 from cotr_b200 import capi
 from cotr_b200.models import build_model
-from oracle import fixtures
+from cotr_b200.utils import synthetic as fixtures
 
 sd = fixtures.make_state_dict(0)
 model = build_model(None)

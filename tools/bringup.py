@@ -223,7 +223,7 @@ def forward_trace():
     import torch
     from cotr_b200 import capi
     from cotr_b200.models import build_model
-    from oracle import fixtures
+    from cotr_b200.utils import synthetic as fixtures
     sd = fixtures.make_state_dict(0)
     model = build_model(None)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
@@ -277,7 +277,7 @@ def launch_profile():
     """Per-launch CUDA-event durations of one eager forward (B=1, Q=1024), library profiler."""
     import torch
     from cotr_b200.models import build_model
-    from oracle import fixtures
+    from cotr_b200.utils import synthetic as fixtures
     sd = fixtures.make_state_dict(0)
     model = build_model(None)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
@@ -327,7 +327,8 @@ def attn_cases(path):
 def model_case(path):
     import torch
     from cotr_b200.models import build_model
-    from oracle import cotr_oracle, fixtures
+    from oracle import cotr_oracle          # bring-up check against the CPU oracle
+    from cotr_b200.utils import synthetic as fixtures
     sd = fixtures.make_state_dict(0)
     img, q = fixtures.make_inputs(1, 1, 1024)
     model = build_model(None)
@@ -357,7 +358,7 @@ def model_case(path):
 def timing():
     import torch
     from cotr_b200.models import build_model
-    from oracle import fixtures
+    from cotr_b200.utils import synthetic as fixtures
     sd = fixtures.make_state_dict(0)
     model = build_model(None)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})

@@ -16,8 +16,8 @@ import torch
 from cotr_b200.inference.sparse_engine import FasterSparseEngine, SparseEngine
 from cotr_b200.models import build_model
 from cotr_b200.utils.utils import fix_randomness
-from oracle import fixtures
-from oracle.fake_model import synthetic_image
+from cotr_b200.utils import synthetic as fixtures
+from cotr_b200.utils.synthetic import synthetic_image
 
 n_queries = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 sd = fixtures.make_state_dict(0)

@@ -2,7 +2,7 @@ import os, sys
 sys.path.insert(0, os.getcwd())
 import torch
 from cotr_b200.models import build_model
-from oracle import fixtures
+from cotr_b200.utils import synthetic as fixtures
 sd = fixtures.make_state_dict(0)
 model = build_model(None)
 model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
