@@ -128,6 +128,11 @@ struct cotr_model {
     std::vector<cudaEvent_t> prof_events;      // 2 per record
     std::vector<cotr_launch_record> prof_records;
     int prof_max = 0;
+    // The workspace, the staging buffers and own_ctx are shared by every entry point: consecutive calls on different
+    // streams are ordered with this event (recorded at the end of each call, waited for by the next call's stream).
+    cudaEvent_t order_event = nullptr;
+    cudaStream_t order_stream = nullptr;
+    bool order_valid = false;
 };
 
 namespace cotr {
@@ -400,6 +405,22 @@ void drop_graphs(cotr_model* m) {
     m->graphs.clear();
     m->graph_launches.clear();
 }
+
+// Cross-stream ordering of the entry points (see cotr_model::order_event).  Same-stream calls need no wait.
+struct CallOrder {
+    cotr_model* m;
+    cudaStream_t s;
+    CallOrder(cotr_model* m_, cudaStream_t s_) : m(m_), s(s_) {
+        if (m->order_valid && m->order_stream != s && m->order_event) cudaStreamWaitEvent(s, m->order_event, 0);
+    }
+    ~CallOrder() {
+        if (!m->order_event && cudaEventCreateWithFlags(&m->order_event, cudaEventDisableTiming) != cudaSuccess) {
+            m->order_event = nullptr;
+            return;
+        }
+        if (cudaEventRecord(m->order_event, s) == cudaSuccess) { m->order_stream = s; m->order_valid = true; }
+    }
+};
 
 int ensure_encode_ws(cotr_model* m, int B) {
     Workspace& w = m->ws;
@@ -798,6 +819,7 @@ void cotr_destroy(cotr_model* m) {
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
     preprocessor_destroy(m->pre);
     for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
+    if (m->order_event) cudaEventDestroy(m->order_event);
     delete m;
 }
 
@@ -825,12 +847,16 @@ void cotr_context_destroy(cotr_context* c) {
 
 int cotr_encode_context(cotr_model* m, const float* img_dev, int B, cotr_context* ctx, void* cuda_stream) {
     COTR_CHECK(m && img_dev, "cotr_encode_context: null argument");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    CallOrder order(m, (cudaStream_t)cuda_stream);
     m->launches = 0;
     return encode_impl(m, img_dev, B, ctx, (cudaStream_t)cuda_stream);
 }
 
 int cotr_decode(cotr_model* m, const cotr_context* ctx, const float* queries_dev, int B, int Q, float* pred_dev, void* cuda_stream) {
     COTR_CHECK(m && (Q == 0 || (queries_dev && pred_dev)), "cotr_decode: null argument");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    CallOrder order(m, (cudaStream_t)cuda_stream);
     m->launches = 0;
     return decode_impl(m, ctx, queries_dev, B, Q, pred_dev, (cudaStream_t)cuda_stream);
 }
@@ -918,6 +944,7 @@ int cotr_forward(cotr_model* m, const float* img_dev, const float* queries_dev, 
     COTR_CHECK(B >= 1 && Q >= 0, "cotr_forward: B must be >= 1 and Q >= 0");
     COTR_CHECK_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
+    CallOrder order(m, s);
     const bool graphable = m->graph_mode && !m->prof_on && (g_tc_timestamps == nullptr || (g_tc_variant & (1 << 17))) && Q > 0;
     if (!graphable) return forward_eager(m, img_dev, queries_dev, B, Q, pred_dev, s);
     // graph replay needs fixed addresses: go through the staging buffers (two small device-to-device copies in, one out)
@@ -939,6 +966,7 @@ int cotr_forward_host(cotr_model* m, const float* img_host, const float* queries
     Workspace& w = m->ws;
     const size_t img_bytes = (size_t)B * 3 * COTR_CANVAS_H * COTR_CANVAS_W * sizeof(float), q_bytes = (size_t)B * Q * 2 * sizeof(float);
     cudaStream_t s = m->host_stream;
+    CallOrder order(m, s);
     COTR_CHECK_CUDA(cudaMemcpyAsync(w.img_stage, img_host, img_bytes, cudaMemcpyHostToDevice, s));
     if (q_bytes) COTR_CHECK_CUDA(cudaMemcpyAsync(w.q_stage, queries_host, q_bytes, cudaMemcpyHostToDevice, s));
     if (Q > 0) {
@@ -954,6 +982,7 @@ int cotr_preprocess(cotr_model* m, const uint8_t* img_from_dev, int h_from, int 
     COTR_CHECK(m != nullptr, "cotr_preprocess: null model");
     COTR_CHECK_CUDA(cudaSetDevice(m->device));
     if (!m->pre) m->pre = preprocessor_create();
+    CallOrder order(m, (cudaStream_t)cuda_stream);
     return preprocess_launch(m->pre, img_from_dev, h_from, w_from, img_to_dev, h_to, w_to, rects_host, n, canvas_dev,
                              (cudaStream_t)cuda_stream);
 }
@@ -1034,10 +1063,7 @@ int cotr_set_gemm_path(cotr_model* m, int path) {
     if (m->gemm_path != path) {          // captured graphs embed the kernels of the old path
         cudaSetDevice(m->device);
         cudaDeviceSynchronize();
-        for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
-    preprocessor_destroy(m->pre);
-        m->graphs.clear();
-        m->graph_launches.clear();
+        drop_graphs(m);
         m->shapes_seen.clear();
     }
     m->gemm_path = path;

@@ -137,7 +137,7 @@ def _dense_pass(model, img_a, img_b):
         out = pred.cpu().numpy()[0].reshape(MAX_SIZE, MAX_SIZE * 2, -1)
     else:
         if hasattr(model, 'encode_context'):
-            ctx = model.encode_context(img)
+            ctx = model.encode_context(img, reuse=True)
             rows = [model.decode(ctx, torch.from_numpy(r)[None].float().to(device))['pred_corrs'].detach().cpu().numpy()[0] for r in grid]
         else:
             rows = [model.forward(img, torch.from_numpy(r)[None].float().to(device))['pred_corrs'].detach().cpu().numpy()[0] for r in grid]
@@ -196,7 +196,7 @@ def _sparse_pass(model, img_a, img_b, queries):
     img = _to_network_canvas(img_a, img_b)[None].to(device)
     q = torch.from_numpy(queries)[None].float().to(device)
     if hasattr(model, 'encode_context'):
-        ctx = model.encode_context(img)
+        ctx = model.encode_context(img, reuse=True)
         out = model.decode(ctx, q)['pred_corrs'].clone().detach()
         cycle = model.decode(ctx, out)['pred_corrs'].clone().detach()
     else:

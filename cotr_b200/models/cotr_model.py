@@ -169,11 +169,13 @@ class COTR(nn.Module):
         backbone.num_channels = 1024
         self.backbone = backbone
         self._native = None
-        self._own_ctx = None
+        self._ctx_cache = {}
 
     # ---- native handle management ---------------------------------------------------------------------
     def _invalidate(self):
-        self._own_ctx = None
+        for ctx in self._ctx_cache.values():
+            ctx.close()
+        self._ctx_cache = {}
         if self._native is not None:
             self._native.close()
         self._native = None
@@ -247,10 +249,22 @@ class COTR(nn.Module):
         return self.native().dense_postprocess(pred)
 
     @torch.no_grad()
-    def encode_context(self, samples):
+    def encode_context(self, samples, reuse=False):
         x = self._canvas(samples)
         nat = self.native()
-        ctx = Context(capi.NativeContext(nat, x.shape[0]), x.shape[0])
+        if reuse:
+            # one cached device K/V buffer per batch size: no cudaMalloc / device-synchronising cudaFree per call.
+            # The returned Context is only valid until the next encode_context(reuse=True) of the same batch size.
+            native_ctx = self._ctx_cache.get(x.shape[0])
+            if native_ctx is None:
+                if len(self._ctx_cache) >= 4:
+                    for old in self._ctx_cache.values():
+                        old.close()
+                    self._ctx_cache = {}
+                native_ctx = self._ctx_cache[x.shape[0]] = capi.NativeContext(nat, x.shape[0])
+        else:
+            native_ctx = capi.NativeContext(nat, x.shape[0])
+        ctx = Context(native_ctx, x.shape[0])
         nat.encode_context(x, ctx.native)
         return ctx
 

@@ -71,9 +71,12 @@ def schema():
     return out
 
 
-def make_state_dict(seed=0, qk_gain=3.0, head_gain=1.35):
+def make_state_dict(seed=0, qk_gain=3.0, head_gain=1.35, stem_gain=1.0):
     """numpy float32 state dict.  Conv: He-normal (fan_out); FrozenBN: random stats; transformer/head:
-    xavier-uniform with q/k rows scaled by `qk_gain` and head matrices by `head_gain`; small biases."""
+    xavier-uniform with q/k rows scaled by `qk_gain` and head matrices by `head_gain`; small biases.
+    `stem_gain` multiplies the 7x7 stem kernel and divides `input_proj.weight`: the whole ResNet body then runs at
+    ~stem_gain times the usual activation magnitude (ReLU networks are positively homogeneous up to the FrozenBN
+    shifts) while the transformer sees ordinary values - the fixture that stresses the fp16 hi/lo storage range."""
     rs = np.random.RandomState(seed)
     sd = {}
     for key, shape in schema():
@@ -100,6 +103,9 @@ def make_state_dict(seed=0, qk_gain=3.0, head_gain=1.35):
         else:                                                   # biases
             w = rs.standard_normal(shape) * 0.05
         sd[key] = np.ascontiguousarray(w, dtype=np.float32)
+    if stem_gain != 1.0:
+        sd["backbone.0.body.conv1.weight"] = np.ascontiguousarray(sd["backbone.0.body.conv1.weight"] * np.float32(stem_gain))
+        sd["input_proj.weight"] = np.ascontiguousarray(sd["input_proj.weight"] / np.float32(stem_gain))
     return sd
 
 

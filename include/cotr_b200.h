@@ -22,7 +22,10 @@
  * non-zero and cotr_last_error() describes the problem (the Python wrapper raises the exception type
  * the reference would: AssertionError for a wrong canvas size, RuntimeError otherwise).
  *
- * Threading: one caller thread per model handle; one handle per device.  No hidden host syncs in the
+ * Threading: one caller thread per model handle; one handle per device.  A model's workspace, staging buffers and
+ * internal context are shared by all its entry points: calls may use different streams (each call makes its stream
+ * wait for the previous call's work through an internal event), but they execute one after the other, and a
+ * cotr_context must not be re-encoded while a decode on it is still in flight on another stream.  No hidden host syncs in the
  * device-pointer calls (work is enqueued on the caller's stream) except when the internal workspace has
  * to grow (first call / larger B or Q than seen before).
  */

@@ -13,10 +13,12 @@ CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.
 
 def _load(golden_dir, name):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    wseed, qk, hg, iseed, b, q = g["params"]
-    sd = fixtures.make_state_dict(int(wseed), float(qk), float(hg))
+    params = g["params"]
+    wseed, qk, hg, iseed, b, q = params[:6]
+    stem_gain, q_stride = (float(params[6]), int(params[7])) if len(params) > 6 else (1.0, 1)   # round-2 cases
+    sd = fixtures.make_state_dict(int(wseed), float(qk), float(hg), stem_gain)
     img, queries = fixtures.make_inputs(int(iseed), int(b), int(q))
-    return g, sd, img, queries
+    return g, sd, img, queries, q_stride
 
 
 def test_golden_files_exist():
@@ -25,16 +27,16 @@ def test_golden_files_exist():
 
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_fp32_matches_reference_fp32(golden_dir, name):
-    g, sd, img, queries = _load(golden_dir, name)
-    pred = cotr_oracle.forward(sd, img, queries, torch.float32).numpy()
+    g, sd, img, queries, q_stride = _load(golden_dir, name)
+    pred = cotr_oracle.forward(sd, img, queries, torch.float32).numpy()[:, ::q_stride]
     # same arithmetic, same library kernels: the restatement reproduces the reference to fp32 round-off
     assert np.abs(pred - g["ref_pred_fp32"]).max() < 5e-6
 
 
 @pytest.mark.parametrize("name", [c for c in CASES if "q1024" not in c])
 def test_oracle_fp64_matches_reference_fp64(golden_dir, name):
-    g, sd, img, queries = _load(golden_dir, name)
-    pred = cotr_oracle.forward(sd, img, queries, torch.float64).numpy()
+    g, sd, img, queries, q_stride = _load(golden_dir, name)
+    pred = cotr_oracle.forward(sd, img, queries, torch.float64).numpy()[:, ::q_stride]
     assert np.abs(pred - g["ref_pred_fp64"]).max() < 1e-10
     assert float(g["oracle_vs_ref_fp64"]) < 1e-10          # recorded when the goldens were generated
 
