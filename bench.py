@@ -11,10 +11,16 @@ inside the timed step (the path's only exchange).
 
 One JSON line on rank 0:
   value      query-points/s, whole job, inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps
-  e2e        same metric through the C-ABI host-buffer call (cotr_forward_host): pinned host buffers, H2D + D2H inside
-  roofline   dominant kernel (by time) from a separate pass with per-launch CUDA events on the launching stream
+  e2e        same metric end to end from pinned HOST buffers: N = 1 through the C-ABI host-buffer call
+             (cotr_forward_host: H2D + forward + D2H inside); N > 1 through the Python API with the NCCL result gather
+             and the D2H read of the gathered (N,1024,2) block inside the timed region
+  roofline   dominant kernel family of the step: its share of the kernel time comes from a per-launch CUDA-event pass
+             (library profiler, eager), its time from share x the TIMED graph-replayed step - so kernel_ms_per_step
+             can never exceed ms_per_step; `whole_step` = algorithmic FLOP / timed step
+  config4    BASELINE.json configs[3] per GPU (8 pairs x 1024 queries in one forward), device-timed, whole-step roofline
   cpu_baseline  the oracle port (CPU restatement of the reference, oracle/cotr_oracle.py) on the host cores, rank 0, N=1
 `--impl reference` times that CPU path alone (all host threads) and prints the same line shape with "impl": "reference".
+`--config 3` / `--config 5` time the zoom-in engines instead.
 """
 import argparse
 import json
@@ -120,6 +126,28 @@ def host_threads():
     return max(1, n)
 
 
+def config_dict(world):
+    """The `config` object of the JSON line - the SAME object in the native and in the reference arm."""
+    return {"workload": WORKLOAD, "pairs_per_gpu": 1, "queries_per_pair": N_QUERIES,
+            "parallelism": f"dp{world} (independent pairs)",
+            "l2": "GPU arm: flushed between timed steps by writing a 256 MiB buffer; CPU arm: not applicable",
+            "weights": "seeded synthetic (cotr_b200/utils/synthetic.py seed 0)",
+            "result_gather": "GPU arm: nccl all_gather of the (N,1024,2) predictions inside the step when N > 1; CPU arm "
+                             "(rank 0 runs one pair per step on the host cores): none"}
+
+
+def committed_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this round (profiles/r02_traffic.json, written by tools/ncu_summary.py)."""
+    path = os.path.join(REPO, "profiles", "r02_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return float(t["gemm_tc"]["dram_bytes_per_launch"]), t.get("source", path)
+    except Exception:
+        return None, "no committed ncu --set full capture for this build"
+
+
 def cpu_reference_rate(budget_s, warmup=1, max_iters=30):
     """The oracle port (validated bit-exact against the reference on CPU) on all host threads, same workload."""
     import torch
@@ -141,6 +169,51 @@ def cpu_reference_rate(budget_s, warmup=1, max_iters=30):
                       f"fp32 eager torch {torch.__version__} on {torch.get_num_threads()} threads (os.cpu_count {os.cpu_count()})"}
 
 
+def cpu_engine_rate(n_queries_full, n_sample=16):
+    """CPU baseline of the engine configs: the oracle port driving the same SparseEngine on a BOUNDED sample (one dense
+    first-guess pass + n_sample forced queries x 4 zoom levels), extrapolated to the full query count."""
+    import contextlib
+    import io
+    import torch
+    from torch import nn
+    from oracle import cotr_oracle, fixtures
+    from cotr_b200.inference.sparse_engine import SparseEngine
+    from cotr_b200.utils.utils import fix_randomness
+    from tools import engine_bench
+    torch.set_num_threads(host_threads())
+
+    class OracleCOTR(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.anchor = nn.Parameter(torch.zeros(1), requires_grad=False)
+            self.sd = cotr_oracle.cast_state_dict(fixtures.make_state_dict(0), torch.float32)
+            self.seconds = []
+
+        @torch.no_grad()
+        def forward(self, img, queries):
+            t0 = time.perf_counter()
+            out = cotr_oracle.forward(self.sd, img, queries, torch.float32)
+            self.seconds.append((int(queries.shape[0]) * int(queries.shape[1]), time.perf_counter() - t0))
+            return {'pred_corrs': out}
+
+    model = OracleCOTR()
+    img_a, img_b = engine_bench._pair()
+    q = engine_bench._queries(n_sample)
+    fix_randomness(0)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        SparseEngine(model, n_sample, mode='tile').cotr_corr_multiscale(img_a, img_b, engine_bench.ZOOMS, 1, max_corrs=n_sample,
+                                                                         queries_a=q.copy(), force=True)
+    total = time.perf_counter() - t0
+    dense = sum(t for n, t in model.seconds if n > 100000)
+    per_step = (total - dense) / (n_sample * 4)
+    full = dense + per_step * n_queries_full * 4
+    return {"value": n_queries_full / full, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle port under the same SparseEngine: 1 dense pass ({dense:.1f} s) + {n_sample} forced queries x 4 zoom levels "
+                      f"({per_step * 1e3:.0f} ms per query-step incl. host PIL work), extrapolated to {n_queries_full} queries "
+                      f"({full:.0f} s); {total:.1f} s of CPU work measured"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
     if rank != 0:
@@ -158,16 +231,34 @@ def run_reference(args, rank, world):
         t0 = time.perf_counter()
         cotr_oracle.forward(sd, img, queries, torch.float32)
         steps.append(time.perf_counter() - t0)
-    ms = float(np.mean(steps)) * 1e3
+    # the host is shared and noisy (round 1: 8.3-9.9 k q/s across records): the median step is the robust figure
+    ms = float(np.median(steps)) * 1e3
     value = N_QUERIES / (ms * 1e-3)
     base = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{args.steps} forwards of 1 pair x 1024 queries per step (the whole workload of one GPU), fp32 eager torch on {torch.get_num_threads()} threads (os.cpu_count {os.cpu_count()})"}
+            "sample": f"{args.steps} forwards of 1 pair x 1024 queries per step (the whole workload of one GPU), median step "
+                      f"(mean {float(np.mean(steps)) * 1e3:.1f} ms, min {float(np.min(steps)) * 1e3:.1f} ms), fp32 eager torch on "
+                      f"{torch.get_num_threads()} threads (os.cpu_count {os.cpu_count()})"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU path does not use the GPUs; one pair per step"},
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
         "cpu_baseline": base, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def _timed_steps(step, flush, n, barrier):
+    """n steps, each bracketed by CUDA events on the launching stream, L2 flushed before each; mean ms per step."""
+    import torch
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+    barrier()
+    for i in range(n):
+        flush.zero_()
+        starts[i].record()
+        step()
+        stops[i].record()
+    barrier()
+    return sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / n
 
 
 def run_native(args, rank, local_rank, world):
@@ -189,6 +280,7 @@ def run_native(args, rank, local_rank, world):
     q_pin = torch.from_numpy(q_np).pin_memory()
     out_pin = torch.empty((1, N_QUERIES, 2), dtype=torch.float32).pin_memory()
     gathered = torch.empty((world, N_QUERIES, 2), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered_pin = torch.empty((world, N_QUERIES, 2), dtype=torch.float32).pin_memory() if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step():
@@ -211,38 +303,61 @@ def run_native(args, rank, local_rank, world):
         sampler.start()
 
     # ---- value: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps ----------
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    for i in range(args.steps):
-        flush.zero_()
-        starts[i].record()
-        step()
-        stops[i].record()
-    barrier()
+    dev_ms = _timed_steps(step, flush, args.steps, barrier)
     launches_per_step = nat.last_launch_count()
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / args.steps
 
-    # ---- e2e: the C-ABI host-buffer call, pinned host memory, H2D + forward + D2H + sync inside ---------------------
+    # ---- e2e: host buffers in, host result out, every copy inside the timed region ----------------------------------
     img_h, q_h, out_h = img_pin.numpy(), q_pin.numpy(), out_pin.numpy()
+    if world == 1:
+        def e2e_step():                      # the C-ABI host-buffer call: H2D + forward + D2H + sync inside
+            nat.forward_host(img_h, q_h, out_h)
+        e2e_api = "cotr_forward_host (C ABI, pinned host buffers)"
+        d2h = int(out_pin.numel() * 4)
+    else:
+        def e2e_step():                      # the multi-GPU job as a user runs it: H2D, forward, NCCL gather, D2H of the gathered block
+            pred = model(img_pin.to(dev, non_blocking=True), q_pin.to(dev, non_blocking=True))["pred_corrs"]
+            dist.all_gather_into_tensor(gathered, pred)
+            gathered_pin.copy_(gathered, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e2e_api = "COTR.forward on pinned host tensors + nccl all_gather + D2H of the gathered (N,1024,2) block"
+        d2h = int(gathered_pin.numel() * 4)
     for _ in range(3):
-        nat.forward_host(img_h, q_h, out_h)
+        e2e_step()
     barrier()
     e2e_times = []
     for i in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        nat.forward_host(img_h, q_h, out_h)
+        e2e_step()
         e2e_times.append(time.perf_counter() - t0)
     barrier()
     e2e_ms = float(np.mean(e2e_times)) * 1e3
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline pass: per-launch events (library profiler), same steps ------------------------------------------
+    # ---- BASELINE.json configs[3] per GPU: 8 pairs x 1024 queries in one forward (64 pairs over 8 GPUs) --------------
+    B4 = 8
+    img4_np, q4_np = fixtures.make_inputs(200 + rank, B4, N_QUERIES)
+    img4 = torch.from_numpy(img4_np).to(dev)
+    q4 = torch.from_numpy(q4_np).to(dev)
+    gathered4 = torch.empty((world * B4, N_QUERIES, 2), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step4():
+        pred = model(img4, q4)["pred_corrs"]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered4, pred)
+
+    for _ in range(3):
+        step4()
+    c4_steps = max(5, min(args.steps, 20))
+    c4_ms = _timed_steps(step4, flush, c4_steps, barrier)
+    c4_launches = nat.last_launch_count()
+
+    # ---- kernel shares: per-launch events (library profiler, eager launches), rank 0 ---------------------------------
     per_kernel = {}
+    prof_steps = min(args.steps, 10)
     if rank == 0:
-        for _ in range(args.steps):
+        for _ in range(prof_steps):
             flush.zero_()
             nat.profile_begin(1024)
             model(img, queries)
@@ -254,10 +369,10 @@ def run_native(args, rank, local_rank, world):
                 elif name.startswith("attention"):
                     d["flop"] += 2.0 * 2.0 * M * N * K        # QK^T + PV over 8 heads x 32 dims
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, c4_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms, c4_ms = t.tolist()
     if rank != 0:
         return
 
@@ -266,35 +381,44 @@ def run_native(args, rank, local_rank, world):
     value = total_q / (dev_ms * 1e-3)
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
     d = per_kernel[dom]
-    achieved_tf = d["flop"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+    share = d["ms"] / sum(v["ms"] for v in per_kernel.values())
+    kernel_ms = dev_ms * share                      # the family's time inside the TIMED (graph-replayed) step
+    achieved_tf = (d["flop"] / prof_steps) / (kernel_ms * 1e-3) / 1e12
     step_tf = algorithmic_flop(1, N_QUERIES) / (dev_ms * 1e-3) / 1e12
+    whole_step = {"algorithmic_gflop": algorithmic_flop(1, N_QUERIES) / 1e9, "achieved": step_tf, "unit": "TFLOP/s",
+                  "frac": step_tf / peaks["bf16_tflops"]}
+    traffic, traffic_src = committed_traffic()
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": achieved_tf / peaks["bf16_tflops"],
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four gemm_tc launches of the committed
-        # `ncu --set full` capture (profiles/r01_final_ncu_summary.md: 2.93 / 1.36 / 1.63 / 3.72 MB read, 0 written;
-        # algorithmic bytes of the same launches 2.8 / 1.3 / 1.6 / 3.4 MB)
-        "traffic": 2.41e6 if dom == "gemm_tc" else None, "traffic_unit": "bytes per launch (ncu capture, not measured live)",
+        "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peaks["source"],
-        "launches_per_step": d["launches"] // args.steps, "kernel_ms_per_step": d["ms"] / args.steps,
-        "kernel_share_of_step": d["ms"] / sum(v["ms"] for v in per_kernel.values()),
-        "whole_step": {"algorithmic_gflop": algorithmic_flop(1, N_QUERIES) / 1e9, "achieved": step_tf, "frac": step_tf / peaks["bf16_tflops"]},
-        "per_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(per_kernel.items())},
-        "note": "algorithmic FLOPs (2*M*N*K per GEMM launch; the 3 split-precision MMAs per product are NOT counted) / summed launch durations; "
-                "measured in a separate pass with per-launch CUDA events on the launching stream",
+        "launches_per_step": d["launches"] // prof_steps, "kernel_ms_per_step": kernel_ms,
+        "kernel_share_of_step": share,
+        "whole_step": whole_step,
+        "eager_pass_ms_per_step": {k: v["ms"] / prof_steps for k, v in sorted(per_kernel.items())},
+        "note": "achieved = algorithmic FLOPs of the family's launches (2*M*N*K per GEMM; the 3 split-precision MMAs per product are NOT "
+                "counted) / (timed step x the family's share of the summed per-launch CUDA-event times of an eager profiling pass); "
+                "eager_pass_ms_per_step are those un-overlapped eager launch times (context only: they exceed the graph-replayed step)",
     }
+    c4_flop = algorithmic_flop(B4, N_QUERIES)
+    c4_tf = c4_flop / (c4_ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (fp16 hi/lo split operands, fp32 accumulate on tcgen05)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_gpu": 1, "queries_per_pair": N_QUERIES, "parallelism": f"dp{world} (independent pairs)",
-                   "l2": "flushed between timed steps by writing a 256 MiB buffer", "weights": "seeded synthetic (cotr_b200/utils/synthetic.py seed 0)",
-                   "result_gather": "nccl all_gather inside the step" if world > 1 else "none (single GPU)"},
+        "config": config_dict(world),
         "e2e": {"value": total_q / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(img_np.nbytes + q_np.nbytes), "d2h_bytes_per_step": int(out_pin.numel() * 4),
-                "api": "cotr_forward_host (C ABI, pinned host buffers)"},
+                "h2d_bytes_per_step": int(img_np.nbytes + q_np.nbytes), "d2h_bytes_per_step": d2h, "api": e2e_api},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
+        "whole_step": whole_step,
+        "config4": {"workload": "configs[3]: 64 independent pairs x 1024 queries over 8 GPUs = 8 pairs per GPU in one forward",
+                    "pairs_per_gpu": B4, "queries_per_pair": N_QUERIES, "value": world * B4 * N_QUERIES / (c4_ms * 1e-3), "unit": UNIT,
+                    "ms_per_step": c4_ms, "steps": c4_steps, "launches_per_step": c4_launches,
+                    "roofline": {"bound": "tensor", "algorithmic_gflop": c4_flop / 1e9, "achieved": c4_tf, "peak": peaks["bf16_tflops"],
+                                 "unit": "TFLOP/s", "frac": c4_tf / peaks["bf16_tflops"]},
+                    "result_gather": "nccl all_gather inside the step" if world > 1 else "none (single GPU)"},
         "clocks": clocks,
     }
     if world == 1:
@@ -308,7 +432,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
+                    help="2 = the headline (default); 3 / 5 = the zoom-in engines of BASELINE.json configs[2] / configs[4]")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: become `torch.distributed.run` with N ranks on this node
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+                                   os.path.abspath(__file__)] + sys.argv[1:])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -318,12 +449,19 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    if args.gpus != world:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but the launcher started {world} rank(s)")
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_native(args, rank, local_rank, world)
+        if args.config != 2:
+            from tools import engine_bench
+            cpu = cpu_engine_rate(10000 if args.config == 3 else int(2048 / 0.3) * 2) if (rank == 0 and world == 1) else None
+            engine_bench.run_config(args.config, rank, local_rank, world, steps=max(1, min(args.steps, 3)), cpu_rate=cpu)
+        else:
+            run_native(args, rank, local_rank, world)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -22,7 +22,7 @@ class CotrTensor(ctypes.Structure):
 class TestGemmDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "path", "M", "N", "K", "a_mode", "lda", "H", "W", "C", "OH", "OW", "KH", "KW", "stride", "pad",
-        "relu", "add_period", "ld_add", "ldr", "ldc")] + [("a_elems", ctypes.c_int64)]
+        "relu", "add_period", "ld_add", "ldr", "ldc", "a_ln", "res_ln", "emit_part", "reserved")] + [("a_elems", ctypes.c_int64)]
 
 
 class LaunchRecord(ctypes.Structure):
@@ -45,6 +45,7 @@ _PROTOTYPES = {
     "cotr_preprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_dense_postprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_rasterize_triangles": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_set_graph_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cotr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "cotr_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -52,7 +53,7 @@ _PROTOTYPES = {
     "cotr_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(LaunchRecord), ctypes.c_int]),
     "cotr_debug_read": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
     "cotr_set_gemm_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
-    "cotr_test_gemm": (ctypes.c_int, [ctypes.POINTER(TestGemmDesc)] + [ctypes.c_void_p] * 8),
+    "cotr_test_gemm": (ctypes.c_int, [ctypes.POINTER(TestGemmDesc)] + [ctypes.c_void_p] * 9),
     "cotr_test_attention": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int]),
     "cotr_debug_set_variant": (None, [ctypes.c_int]),
     "cotr_debug_set_timestamps": (None, [ctypes.c_void_p]),
@@ -229,9 +230,21 @@ class NativeModel:
             pass
 
 
+def rasterize_triangles(tris, H, W):
+    """(n_tri,3,4) fp32 CUDA tensor [x, y, u, v] per vertex -> (H,W,2) fp32 CUDA tensor (cotr_rasterize_triangles)."""
+    tris = tris.contiguous()
+    assert tris.is_cuda and tris.dtype == torch.float32 and tris.ndim == 3 and tris.shape[1:] == (3, 4)
+    out = torch.empty((H, W, 2), dtype=torch.float32, device=tris.device)
+    dev = tris.device.index if tris.device.index is not None else torch.cuda.current_device()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib().cotr_rasterize_triangles(dev, _ptr(tris), tris.shape[0], int(H), int(W), _ptr(out), stream), "cotr_rasterize_triangles")
+    return out
+
+
 def test_gemm(path, A, w_host, *, bias=None, addmat=None, add_period=1, residual=None, relu=False, ln=None,
-              a_mode=0, conv=None, M=None, ldc=None):
-    """Kernel-level hook: out = epilogue(A W^T).  A and optional epilogue operands are CUDA fp32 tensors."""
+              a_mode=0, conv=None, M=None, ldc=None, a_ln=False, res_ln=False, part_out=None):
+    """Kernel-level hook: out = epilogue(A W^T).  A and optional epilogue operands are CUDA fp32 tensors.
+    a_ln / res_ln: `ln` = (gamma, beta) is a DEFERRED LayerNorm of the A rows / of the residual rows (tcgen05 path)."""
     N, K = w_host.shape
     d = TestGemmDesc()
     d.path = path
@@ -247,6 +260,9 @@ def test_gemm(path, A, w_host, *, bias=None, addmat=None, add_period=1, residual
         d.lda = conv.get("C", 0) if a_mode != 3 else A.shape[-1]
     d.a_elems = A.numel()
     d.relu = int(relu)
+    d.a_ln = int(a_ln)
+    d.res_ln = int(res_ln)
+    d.emit_part = int(part_out is not None)
     d.add_period = add_period
     d.ld_add = addmat.stride(0) if addmat is not None else 0
     d.ldr = residual.stride(0) if residual is not None else 0
@@ -255,7 +271,7 @@ def test_gemm(path, A, w_host, *, bias=None, addmat=None, add_period=1, residual
     w_np = np.ascontiguousarray(w_host, np.float32)
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     check(lib().cotr_test_gemm(ctypes.byref(d), p(A), ctypes.c_void_p(w_np.ctypes.data), p(bias), p(addmat), p(residual),
-                               p(ln[0]) if ln else None, p(ln[1]) if ln else None, p(out)), "cotr_test_gemm")
+                               p(ln[0]) if ln else None, p(ln[1]) if ln else None, p(out), p(part_out)), "cotr_test_gemm")
     return out
 
 

@@ -167,6 +167,19 @@ struct GemmParams {
     int relu;
     const float* ln_gamma;   // optional LayerNorm over the N = 256 columns of each row (after the residual)
     const float* ln_beta;
+    // Deferred LayerNorm (tcgen05 path, row-major A).  A LayerNorm output is never stored: the GEMM that produces the
+    // PRE-norm rows x (N = 256) also leaves, per row and 16-column chunk, the chunk's (mean, M2) in `ln_part_out`
+    // [M][16] float2 (from the fp32 values in its epilogue registers); every consumer merges the 16 pairs into the row's
+    // (mean, rstd) in its own epilogue prologue and applies the norm on the fly:
+    //   * as the A operand (K = 256): the weights carry gamma (W' = W diag(gamma), packed at model creation) and
+    //         y[n] = rstd * (acc[n] - mean * a_ln_cs[n]) + bias[n],   a_ln_cs[n] = sum_k W'[n,k],  bias = beta W^T + b;
+    //   * as the residual operand: res[n] = (r[n] - mean) rstd res_ln_gamma[n] + res_ln_beta[n].
+    const float* a_ln_cs;          // [N]; null = A is used as it is stored
+    const float2* a_ln_part;       // [M][16] partial statistics of the A rows
+    const float2* res_ln_part;     // [M][16] partial statistics of the residual rows; null = plain residual
+    const float* res_ln_gamma;
+    const float* res_ln_beta;
+    float2* ln_part_out;           // [M][16]; null = no statistics wanted
     // outputs
     float* out_f32;          // when non-null: plain fp32 row-major output (the final prediction, N = 2)
     Split16 out;             // otherwise split16, row-major with leading dimension ldc ...
@@ -201,12 +214,19 @@ int launch_attention_simt(const AttnParams& p, cudaStream_t s);
 int launch_attention_tc(const AttnParams& p, cudaStream_t s);
 int launch_maxpool_3x3s2_nhwc(CSplit16 in, Split16 out, int N, int H, int W, int C, cudaStream_t s);
 int launch_layernorm(CSplit16 x, const float* gamma, const float* beta, Split16 out, int rows, cudaStream_t s);
+// out = LN2(LN1(x)): the last decoder layer's norm3 followed by decoder.norm (transformer.py:110-111) in one pass
+// part[row][c] = (mean, M2) of channels [16c, 16c+16) of a [rows][256] tensor (what GemmParams::ln_part_out holds)
+int launch_ln_partials(CSplit16 x, float2* part, int rows, cudaStream_t s);
+int launch_layernorm_twice(CSplit16 x, const float* g1, const float* b1, const float* g2, const float* b2, Split16 out, int rows, cudaStream_t s);
 int launch_query_encode(const float* queries, Split16 qpos, int rows, cudaStream_t s);
 int launch_f32_to_split16(const float* in, Split16 out, size_t n, cudaStream_t s);
 int launch_split16_to_f32(CSplit16 in, float* out, size_t n, cudaStream_t s);
 
 // Device-side post-processing of the dense pass (dense_post.cu)
 int dense_post_launch(const float* pred, float* out, int n, cudaStream_t s);
+
+// Barycentric triangle rasteriser of triangulate_corr (engine_ops.cu)
+int rasterize_triangles_launch(const float* tris, int n_tri, int H, int W, float* out, cudaStream_t s);
 
 // Device-side crop + Pillow-exact resize + normalise (preprocess.cu)
 struct Preprocessor;

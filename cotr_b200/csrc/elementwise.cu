@@ -47,6 +47,64 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // out = LayerNorm(x) over 256 channels, eps 1e-5, biased variance.  One warp per row, 8 channels per lane.
+__device__ __forceinline__ void load_vec8(const float* __restrict__ p, int lane, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + lane * 8)), b = __ldg(reinterpret_cast<const float4*>(p + lane * 8 + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// v (8 channels per lane of one warp) <- LayerNorm over the 256 channels of the row
+__device__ __forceinline__ void warp_layernorm256(float (&v)[8], const float* __restrict__ gamma, const float* __restrict__ beta, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    const float mean = warp_sum(s) * (1.f / kDModel);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] -= mean; sq = fmaf(v[j], v[j], sq); }
+    const float rstd = 1.f / sqrtf(warp_sum(sq) * (1.f / kDModel) + 1e-5f);
+    float g[8], b[8];
+    load_vec8(gamma, lane, g);
+    load_vec8(beta, lane, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * rstd * g[j] + b[j];
+}
+
+// (mean, M2) of every 16-channel chunk of a row: two neighbouring lanes (8 channels each) share a chunk
+__global__ void __launch_bounds__(256) ln_partials_kernel(const CSplit16 x, float2* __restrict__ part, int rows) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    float v[8];
+    load8_split(x, (size_t)warp * kDModel + lane * 8, v);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    const float mean = s * (1.f / 16.f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; m2 = fmaf(d, d, m2); }
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+    if ((lane & 1) == 0) part[(size_t)warp * 16 + (lane >> 1)] = make_float2(mean, m2);
+}
+
+// out = LN_b(LN_a(x)), one warp per row (the decoder's last norm3 followed by decoder.norm)
+__global__ void __launch_bounds__(256) layernorm256_twice_kernel(const CSplit16 x, const float* __restrict__ g1, const float* __restrict__ b1,
+                                                                 const float* __restrict__ g2, const float* __restrict__ b2,
+                                                                 const Split16 out, int rows) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    pdl_wait();
+    if (warp >= rows) return;
+    const size_t off = (size_t)warp * kDModel + lane * 8;
+    float v[8];
+    load8_split(x, off, v);
+    warp_layernorm256(v, g1, b1, lane);
+    warp_layernorm256(v, g2, b2, lane);
+    store8_split(out, off, v);
+}
+
 template <bool F32_IN>
 __global__ void __launch_bounds__(256) layernorm256_kernel(const CSplit16 x, const float* __restrict__ x_f32,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -59,8 +117,8 @@ __global__ void __launch_bounds__(256) layernorm256_kernel(const CSplit16 x, con
     const size_t off = (size_t)warp * kDModel + lane * 8;
     float v[8];
     if constexpr (F32_IN) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(x_f32 + off));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(x_f32 + off + 4));
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(x_f32 + off));
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(x_f32 + off + 4));
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
         load8_split(x, off, v);
@@ -135,6 +193,19 @@ int launch_maxpool_3x3s2_nhwc(CSplit16 in, Split16 out, int N, int H, int W, int
 int launch_layernorm(CSplit16 x, const float* gamma, const float* beta, Split16 out, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
     COTR_CHECK_CUDA(launch_kernel(layernorm256_kernel<false>, dim3((rows + 7) / 8), dim3(256), 0, s, x, (const float*)nullptr, gamma, beta, out, rows));
+    return 0;
+}
+
+int launch_ln_partials(CSplit16 x, float2* part, int rows, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    ln_partials_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, part, rows);
+    COTR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_layernorm_twice(CSplit16 x, const float* g1, const float* b1, const float* g2, const float* b2, Split16 out, int rows, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    COTR_CHECK_CUDA(launch_kernel(layernorm256_twice_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g1, b1, g2, b2, out, rows));
     return 0;
 }
 

@@ -16,8 +16,8 @@ __device__ __forceinline__ float4 load_a4_f32(const GemmParams& p, const ARow& r
     size_t off;
     if (!a_offset8(p, r, k & ~7, off)) return v;     // all split16 operands have K % 8 == 0
     off += (k & 4);
-    const uint2 h = __ldg(reinterpret_cast<const uint2*>(p.a.hi + off));
-    const uint2 l = __ldg(reinterpret_cast<const uint2*>(p.a.lo + off));
+    const uint2 h = __ldcg(reinterpret_cast<const uint2*>(p.a.hi + off));
+    const uint2 l = __ldcg(reinterpret_cast<const uint2*>(p.a.lo + off));
     const float2 a = join_f16x2(h.x, l.x), b = join_f16x2(h.y, l.y);
     return make_float4(a.x, a.y, b.x, b.y);
 }

@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     uint64_t* accum_full = bars + 3 * C::kStages;
     uint64_t* part_full = bars + 3 * C::kStages + 1;       // split-K leader: all peers' partial tiles have landed
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 2);
+    // deferred LayerNorm (GemmParams::a_ln_cs / res_ln_part / ln_part_out): only the row-major loader instantiations carry it
+    constexpr bool kCanLnA = (MODE == LD_GATHER) && !LN;
+    const bool has_aln = kCanLnA && p.a_ln_cs != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
@@ -340,6 +343,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         const bool has_res = row_ok && p.res.hi != nullptr;
         const size_t res_off = (size_t)(row_ok ? row : 0) * p.ldr;
         const float acc_scale = p.acc_scale;
+        // Deferred LayerNorm: (mean, rstd) of a 256-wide row from the 16 partial statistics its producer's epilogue
+        // left behind (one (mean, M2) pair per 16-column chunk, GemmParams::ln_part_out), merged exactly (Chan et al.):
+        // M2 = sum M2_i + 16 sum (mean_i - mean)^2.  One 128-byte line per row, read with ld.global.cg (never .nc: the
+        // producer is a kernel that may still have been running when this one became resident, see load8_split),
+        // issued here - before the accumulator is ready - so the latency hides behind the main loop.
+        auto row_stats = [&](const float2* part) {
+            float2 pr[16];
+            const float4* src = reinterpret_cast<const float4*>(part + (size_t)row * 16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t4 = __ldcg(src + j);
+                pr[2 * j] = make_float2(t4.x, t4.y);
+                pr[2 * j + 1] = make_float2(t4.z, t4.w);
+            }
+            float mean = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mean += pr[j].x;
+            mean *= (1.f / 16.f);
+            float m2 = 0.f, dev = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                m2 += pr[j].y;
+                const float d = pr[j].x - mean;
+                dev = fmaf(d, d, dev);
+            }
+            const float var = fmaf(16.f, dev, m2) * (1.f / 256.f);
+            return make_float2(mean, 1.f / sqrtf(var + 1e-5f));
+        };
+        const bool res_ln = kCanLnA && has_res && p.res_ln_part != nullptr;
+        float2 res_st = make_float2(0.f, 1.f);
+        if (kCanLnA && res_ln) res_st = row_stats(p.res_ln_part);
+        float2 a_st = make_float2(0.f, 1.f);            // (mean, rstd) of this thread's A row
+        if (kCanLnA && has_aln && row_ok) a_st = row_stats(p.a_ln_part);
+        const bool emit_part = kCanLnA && row_ok && p.ln_part_out != nullptr;
         const bool tail = p.out_f32 != nullptr && (p.N & 15) != 0;      // only the N = 2 prediction head
         const bool has_bias = p.bias != nullptr && !tail;
 
@@ -357,12 +394,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             if (has_res) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    o.res_hi[j] = __ldg(reinterpret_cast<const uint4*>(p.res.hi + res_off + nb) + j);
-                    o.res_lo[j] = __ldg(reinterpret_cast<const uint4*>(p.res.lo + res_off + nb) + j);
+                    o.res_hi[j] = __ldcg(reinterpret_cast<const uint4*>(p.res.hi + res_off + nb) + j);
+                    o.res_lo[j] = __ldcg(reinterpret_cast<const uint4*>(p.res.lo + res_off + nb) + j);
                 }
             }
         };
-        auto apply = [&](const EpiOperands& o, float (&v)[16]) {
+        auto apply = [&](const EpiOperands& o, float (&v)[16], int nb) {
+            if (kCanLnA && has_aln) {                 // y = rstd * (x W'^T - mean * colsum(W'))
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 cs4 = __ldg(reinterpret_cast<const float4*>(p.a_ln_cs + nb) + j);
+                    v[4 * j] = a_st.y * fmaf(-a_st.x, cs4.x, v[4 * j]);
+                    v[4 * j + 1] = a_st.y * fmaf(-a_st.x, cs4.y, v[4 * j + 1]);
+                    v[4 * j + 2] = a_st.y * fmaf(-a_st.x, cs4.z, v[4 * j + 2]);
+                    v[4 * j + 3] = a_st.y * fmaf(-a_st.x, cs4.w, v[4 * j + 3]);
+                }
+            }
             if (has_bias) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { v[4 * j] += o.bias[j].x; v[4 * j + 1] += o.bias[j].y; v[4 * j + 2] += o.bias[j].z; v[4 * j + 3] += o.bias[j].w; }
@@ -378,7 +425,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     const uint32_t l[4] = {o.res_lo[j].x, o.res_lo[j].y, o.res_lo[j].z, o.res_lo[j].w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float2 f = join_f16x2(h[q], l[q]);
+                        float2 f = join_f16x2(h[q], l[q]);
+                        if (kCanLnA && res_ln) {      // the residual is a deferred LayerNorm of the stored rows
+                            const float2 g2 = __ldg(reinterpret_cast<const float2*>(p.res_ln_gamma + nb + 8 * j + 2 * q));
+                            const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.res_ln_beta + nb + 8 * j + 2 * q));
+                            f.x = fmaf((f.x - res_st.x) * res_st.y, g2.x, b2.x);
+                            f.y = fmaf((f.y - res_st.x) * res_st.y, g2.y, b2.y);
+                        }
                         v[8 * j + 2 * q] += f.x;
                         v[8 * j + 2 * q + 1] += f.y;
                     }
@@ -561,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 }
                 if (threadIdx.x == 0 && ci < 2) COTR_TS(30 + 4 * ci);
                 if (BN > 16 || !tail) {                          // (a ragged N only exists in the 16-wide instantiation)
-                    apply(ops[ci % C::kRing], v);
+                    apply(ops[ci % C::kRing], v, nb);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)                 // static indexing keeps v[] in registers
@@ -570,6 +623,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (kCanLnA && emit_part) {
+                    // (mean, M2) of these 16 final values for the consumers' deferred LayerNorm
+                    float sm = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sm += v[j];
+                    sm *= (1.f / 16.f);
+                    float m2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float d = v[j] - sm; m2 = fmaf(d, d, m2); }
+                    p.ln_part_out[(size_t)row * 16 + (nb >> 4)] = make_float2(sm, m2);
                 }
                 if (threadIdx.x == 0 && ci < 2) COTR_TS(31 + 4 * ci);
                 emit16(c, v);
@@ -588,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 const int c = ci * 16;
                 float v[16];
                 load_acc(c, v);
-                apply(ops[ci % C::kRing], v);
+                apply(ops[ci % C::kRing], v, c);
                 if (ci + C::kRing < C::kChunksN) prefetch(c + 16 * C::kRing, ops[ci % C::kRing]);
                 if (ci == 0) shift = v[0];
 #pragma unroll
@@ -662,6 +726,11 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
             else if (C::kMaxSplit >= 2 && kc % 2 == 0 && ctas * 2 <= 160) ksplit = 2;
         }
     }
+    COTR_CHECK(p.a_ln_cs == nullptr || (MODE == LD_GATHER && !LN && p.K == 256 && p.a_mode == A_ROWMAJOR && p.a_ln_part != nullptr),
+               "gemm_tc: the deferred LayerNorm on A needs a row-major operand with K = 256 and its partial statistics");
+    COTR_CHECK((p.res_ln_part == nullptr && p.ln_part_out == nullptr) || (MODE == LD_GATHER && !LN),
+               "gemm_tc: deferred-LayerNorm residual / statistics on an unsupported tile");
+    COTR_CHECK(p.ln_part_out == nullptr || (p.N == 256 && !p.remap && p.out_f32 == nullptr), "gemm_tc: row statistics need a plain N = 256 output");
     grid.z = ksplit;
     const size_t smem = C::kSmemBytes + (size_t)(ksplit - 1) * (BM / ksplit) * C::kPartPitch;     // incoming partial rows
     COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), smem, s, ksplit, p, npad, next_trace_block()));

@@ -45,6 +45,10 @@ struct DevLinear {
     float wtc_scale = 1.f;
     float* b = nullptr;    // [N] or null
     int n = 0, k = 0;
+    // Deferred LayerNorm on the input (tensor-core path, GemmParams::a_ln_cs): wtc then holds W diag(gamma),
+    // cs its column sums and b_tc = beta W^T + b; w / b stay the checkpoint's values for the fp32 SIMT path.
+    float* cs = nullptr;
+    float* b_tc = nullptr;
 };
 
 struct Block {
@@ -55,9 +59,11 @@ struct Block {
 struct EncLayer {
     DevLinear qkv;         // [768][256]; q rows pre-scaled by head_dim^-0.5; bias folded into add_qkv
     float* add_qkv = nullptr;   // [512][768] = [ (pos Wq^T + bq) s | pos Wk^T + bk | bv ]
+    float* add_qkv_tc = nullptr;   // + beta W^T of the previous layer's norm2 (deferred LayerNorm, layers > 0)
     DevLinear o, l1, l2;
     float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
 };
+static_assert(sizeof(float2) == 8, "row statistics are (mean, rstd) pairs");
 
 struct DecLayer {
     DevLinear q;           // [256][256] pre-scaled, no bias (bias lives in the qpos projection)
@@ -75,10 +81,12 @@ struct Workspace {
     // encoder
     Split16 src = kNoSplit, xa = kNoSplit, xb = kNoSplit, qk = kNoSplit, vt = kNoSplit, ao = kNoSplit, ffh = kNoSplit;
     float* ln_tmp = nullptr;      // fp32 [tokens][256]: pre-LayerNorm rows of the SIMT cross-check path
+    float2 *enc_st_a = nullptr, *enc_st_b = nullptr;     // [tokens][16] partial row statistics of xa / xb (deferred LayerNorms)
     // decoder
     Split16 qpos = kNoSplit, qp = kNoSplit, t = kNoSplit, qb = kNoSplit, dao = kNoSplit, dh = kNoSplit, hs = kNoSplit,
-            hd1 = kNoSplit, hd2 = kNoSplit;
+            hd1 = kNoSplit, hd2 = kNoSplit, t2 = kNoSplit;
     float* dln_tmp = nullptr;
+    float2 *dec_st_a = nullptr, *dec_st_b = nullptr;
     // host-buffer entry point staging
     float *img_stage = nullptr, *q_stage = nullptr, *pred_stage = nullptr;
     size_t img_stage_elems = 0, q_stage_elems = 0;
@@ -106,6 +114,7 @@ struct cotr_model {
     cotr::EncLayer enc[cotr::kEncLayers];
     cotr::DevLinear kv_all;     // [3072][256] rows [l*512, l*512+256) = Wk_l, [l*512+256, l*512+512) = Wv_l
     float* add_kv = nullptr;    // [512][3072]
+    float* add_kv_tc = nullptr; // + beta W^T of the last encoder norm2 (deferred LayerNorm)
     cotr::DevLinear qpos_all;   // [1536][256] pre-scaled, bias pre-scaled
     cotr::DecLayer dec[cotr::kDecLayers];
     float *dec_norm_g = nullptr, *dec_norm_b = nullptr;
@@ -116,6 +125,7 @@ struct cotr_model {
     cudaStream_t host_stream = nullptr;
     cotr::Split16 last_feat = cotr::kNoSplit;
     cotr::Split16 last_mem = cotr::kNoSplit;
+    bool last_mem_pre_ln = false;   // tensor-core path: last_mem holds the rows BEFORE the last encoder norm2
     int last_pairs = 0, last_rows = 0;
     // per-launch profiler (cotr_profile_begin / cotr_profile_end): CUDA event pairs on the launching stream
     // CUDA-graph replay of cotr_forward, one executable graph per (B, Q) shape (captured on the second call)
@@ -184,6 +194,31 @@ int make_linear(cotr_model* m, const std::vector<float>& w, const std::vector<fl
     if (upload(m, w, &out->w)) return 1;
     if (upload_tc(m, w, N, K, &out->wtc, &out->wtc_scale)) return 1;
     if (b) { if (upload(m, *b, &out->b)) return 1; }
+    return 0;
+}
+
+// Linear layer whose input is a deferred LayerNorm (gamma, beta): tensor-core image of W diag(gamma), its column sums
+// and the folded bias beta W^T + b (see GemmParams::a_ln_cs).
+int make_linear_ln(cotr_model* m, const std::vector<float>& w, const std::vector<float>* b, int N, int K,
+                   const float* gamma, const float* beta, DevLinear* out, std::vector<float>* folded_bias = nullptr) {
+    out->n = N; out->k = K;
+    if (upload(m, w, &out->w)) return 1;
+    if (b) { if (upload(m, *b, &out->b)) return 1; }
+    std::vector<float> wg((size_t)N * K), cs(N), cb(N);
+    for (int n = 0; n < N; ++n) {
+        double s = 0.0, c = b ? (double)(*b)[n] : 0.0;
+        for (int k = 0; k < K; ++k) {
+            const float v = w[(size_t)n * K + k] * gamma[k];
+            wg[(size_t)n * K + k] = v;
+            s += (double)v;
+            c += (double)w[(size_t)n * K + k] * (double)beta[k];
+        }
+        cs[n] = (float)s;
+        cb[n] = (float)c;
+    }
+    if (upload_tc(m, wg, N, K, &out->wtc, &out->wtc_scale)) return 1;
+    if (upload(m, cs, &out->cs) || upload(m, cb, &out->b_tc)) return 1;
+    if (folded_bias) *folded_bias = cb;
     return 0;
 }
 
@@ -337,6 +372,24 @@ int run_linear(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda, Spl
     return run_gemm(r, p, ln_scratch);
 }
 
+// Tensor-core path only: linear layer with deferred LayerNorms (GemmParams::a_ln_cs / res_ln_part / ln_part_out).
+//   a_part     non-null: A holds pre-LayerNorm rows with these partial statistics; L was built by make_linear_ln
+//   part_out   non-null: the output rows are pre-LayerNorm rows of a later norm - leave their partial statistics here
+//   res_part   non-null: the residual operand is a deferred LayerNorm (res_g, res_b) of the stored rows
+int run_linear_dln(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda, Split16 out, int ldc, bool relu,
+                   const float2* a_part, float2* part_out, CSplit16 residual = CSplit16{nullptr, nullptr}, int ldr = 0,
+                   const float2* res_part = nullptr, const float* res_g = nullptr, const float* res_b = nullptr) {
+    GemmParams p = gemm_base(M, L.n, L.k, A, lda, L.w, L.wtc, L.wtc_scale, out, ldc);
+    p.bias = a_part ? L.b_tc : L.b;
+    p.relu = relu ? 1 : 0;
+    p.res = residual; p.ldr = ldr;
+    if (a_part) { p.a_ln_cs = L.cs; p.a_ln_part = a_part; }
+    p.ln_part_out = part_out;
+    p.res_ln_part = res_part; p.res_ln_gamma = res_g; p.res_ln_beta = res_b;
+    LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
+    return launch_gemm_tc(p, r.s);
+}
+
 int run_conv(const Run& r, const DevConv& c, int n_img, CSplit16 in, const float* in_f32, int H, int W, Split16 out,
              bool relu, CSplit16 residual) {
     const int OH = (H + 2 * c.pad - c.kh) / c.stride + 1;
@@ -377,10 +430,10 @@ size_t encode_ws_elems(int B) {
     const size_t img = 2 * (size_t)B;
     const size_t tok = (size_t)B * kTokens;
     return img * (kStemElems + 3 * kBigElems + kT1Elems + kT2Elems) + tok * (kDModel * 4 + 2 * kDModel + kFF) +
-           (size_t)B * kVtLayer + tok * kDModel /* fp32 LN scratch */;
+           (size_t)B * kVtLayer + tok * kDModel /* fp32 LN scratch */ + tok * 64 /* row statistics */;
 }
 size_t decode_ws_elems(int rows) {
-    return (size_t)rows * (kDModel * 7 + kQpCols + kFF) + (size_t)rows * kDModel /* fp32 LN scratch */;
+    return (size_t)rows * (kDModel * 8 + kQpCols + kFF) + (size_t)rows * kDModel /* fp32 LN scratch */ + (size_t)rows * 64 /* row statistics */;
 }
 
 // split16 buffer of `elems` elements: one allocation, hi plane first (elems is always a multiple of 8)
@@ -430,12 +483,15 @@ int ensure_encode_ws(cotr_model* m, int B) {
     Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh};
     for (Split16* b : bufs) ws_free(b);
     ws_free_f32(&w.ln_tmp);
+    ws_free_f32(reinterpret_cast<float**>(&w.enc_st_a));
+    ws_free_f32(reinterpret_cast<float**>(&w.enc_st_b));
     const size_t img = 2 * (size_t)B, tok = (size_t)B * kTokens;
     if (ws_alloc(&w.stem, img * kStemElems) || ws_alloc(&w.bx, img * kBigElems) || ws_alloc(&w.by, img * kBigElems) ||
         ws_alloc(&w.bds, img * kBigElems) || ws_alloc(&w.bt1, img * kT1Elems) || ws_alloc(&w.bt2, img * kT2Elems) ||
         ws_alloc(&w.src, tok * kDModel) || ws_alloc(&w.xa, tok * kDModel) || ws_alloc(&w.xb, tok * kDModel) ||
         ws_alloc(&w.qk, tok * 2 * kDModel) || ws_alloc(&w.vt, (size_t)B * kVtLayer) || ws_alloc(&w.ao, tok * kDModel) ||
-        ws_alloc(&w.ffh, tok * kFF) || ws_alloc_f32(&w.ln_tmp, tok * kDModel))
+        ws_alloc(&w.ffh, tok * kFF) || ws_alloc_f32(&w.ln_tmp, tok * kDModel) ||
+        ws_alloc_f32(reinterpret_cast<float**>(&w.enc_st_a), tok * 32) || ws_alloc_f32(reinterpret_cast<float**>(&w.enc_st_b), tok * 32))
         return 1;
     w.cap_pairs = B;
     return 0;
@@ -446,14 +502,17 @@ int ensure_decode_ws(cotr_model* m, int rows) {
     if (rows <= w.cap_rows) return 0;
     COTR_CHECK_CUDA(cudaDeviceSynchronize());
     drop_graphs(m);
-    Split16* bufs[] = {&w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2};
+    Split16* bufs[] = {&w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2, &w.t2};
     for (Split16* b : bufs) ws_free(b);
     ws_free_f32(&w.dln_tmp);
+    ws_free_f32(reinterpret_cast<float**>(&w.dec_st_a));
+    ws_free_f32(reinterpret_cast<float**>(&w.dec_st_b));
     const size_t R = ((size_t)rows + 7) & ~(size_t)7;
     if (ws_alloc(&w.qpos, R * kDModel) || ws_alloc(&w.qp, R * kQpCols) || ws_alloc(&w.t, R * kDModel) ||
         ws_alloc(&w.qb, R * kDModel) || ws_alloc(&w.dao, R * kDModel) || ws_alloc(&w.dh, R * kFF) ||
         ws_alloc(&w.hs, R * kDModel) || ws_alloc(&w.hd1, R * kDModel) || ws_alloc(&w.hd2, R * kDModel) ||
-        ws_alloc_f32(&w.dln_tmp, R * kDModel))
+        ws_alloc(&w.t2, R * kDModel) || ws_alloc_f32(&w.dln_tmp, R * kDModel) ||
+        ws_alloc_f32(reinterpret_cast<float**>(&w.dec_st_a), R * 32) || ws_alloc_f32(reinterpret_cast<float**>(&w.dec_st_b), R * 32))
         return 1;
     w.cap_rows = rows;
     return 0;
@@ -512,8 +571,67 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
 
     // transformer.py:143-159 x6 (post-LN).  q = k = x + pos is folded into the constant add_qkv matrix.
     // q | k land row-major in qk [T][512]; v lands transposed in vt [pair][256][512] (what P V needs as its B operand).
-    Split16 xin = w.src;      // layer input; norm1 output goes to xa, norm2 output (next input) to xb
-    for (int l = 0; l < kEncLayers; ++l) {
+    Split16 xin = w.src;      // layer input
+    if (m->gemm_path == 0) {
+        // Tensor-core path: no LayerNorm kernel and no LayerNorm epilogue.  A LayerNorm output is never stored; its
+        // producer writes the pre-norm rows (xa: x + attention, xb: x1 + FFN) and every consumer applies the norm on
+        // the fly (GemmParams::a_ln_cs for GEMM inputs, res_ln_part for residual operands) from the partial row
+        // statistics the producer's epilogue leaves behind: enc_st_a belongs to xa (norm1), enc_st_b to xb (norm2).
+        const int n_enc_dbg = (g_tc_variant >> 20) & 7;        // bring-up: stop after this many encoder layers (0 = all)
+        for (int l = 0; l < (n_enc_dbg ? n_enc_dbg : kEncLayers); ++l) {
+            const EncLayer& e = m->enc[l];
+            const bool ln_in = l > 0;          // the layer input is LN2_{l-1}(xb), deferred
+            {
+                GemmParams p = gemm_base(T, 3 * kDModel, kDModel, cs(xin), kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, w.qk, 2 * kDModel);
+                p.addmat = e.add_qkv_tc; p.add_period = kTokens; p.ld_add = 3 * kDModel;
+                p.remap = 1;
+                p.blk_map[0] = 0; p.blk_map[1] = kDModel; p.blk_map[2] = -1;
+                p.vt = w.vt; p.n_vt = 1;
+                if (ln_in) { p.a_ln_cs = e.qkv.cs; p.a_ln_part = w.enc_st_b; }
+                LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
+                if (launch_gemm_tc(p, r.s)) return 1;
+            }
+            AttnParams a;
+            a.q = cs(w.qk); a.ldq = 2 * kDModel;
+            a.k = offset(cs(w.qk), kDModel); a.ldk = 2 * kDModel;
+            a.vt = cs(w.vt); a.vt_pair_stride = kVtLayer;
+            a.out = w.ao; a.ldo = kDModel;
+            a.nq = kTokens; a.npairs = B; a.pair0 = 0;
+            if (run_attention(r, a)) return 1;
+            // xa = x + out_proj(attn)                                   (transformer.py:149-154, norm1 deferred)
+            if (run_linear_dln(r, e.o, T, cs(w.ao), kDModel, w.xa, kDModel, false, nullptr, w.enc_st_a, cs(xin), kDModel,
+                               ln_in ? w.enc_st_b : nullptr, ln_in ? m->enc[l - 1].ln2_g : nullptr, ln_in ? m->enc[l - 1].ln2_b : nullptr)) return 1;
+            // h = relu(W1 norm1(xa) + b1)                               (transformer.py:155)
+            if (run_linear_dln(r, e.l1, T, cs(w.xa), kDModel, w.ffh, kFF, true, w.enc_st_a, nullptr)) return 1;
+            // xb = norm1(xa) + W2 h + b2                                (transformer.py:155-157, norm2 deferred)
+            if (run_linear_dln(r, e.l2, T, cs(w.ffh), kFF, w.xb, kDModel, false, nullptr, w.enc_st_b, cs(w.xa), kDModel,
+                               w.enc_st_a, e.ln1_g, e.ln1_b)) return 1;
+            xin = w.xb;
+        }
+        m->last_mem = xin;
+        m->last_mem_pre_ln = true;
+        // K / V projections of all 6 decoder layers from norm2(xb) of the last encoder layer (deferred as well)
+        {
+            GemmParams p = gemm_base(T, 2 * kKCols, kDModel, cs(xin), kDModel, m->kv_all.w, m->kv_all.wtc, m->kv_all.wtc_scale, ctx->k, kKCols);
+            p.addmat = m->add_kv_tc; p.add_period = kTokens; p.ld_add = 2 * kKCols;
+            p.remap = 1;
+            for (int l = 0; l < kDecLayers; ++l) {
+                p.blk_map[2 * l] = l * kDModel;
+                p.blk_map[2 * l + 1] = -(l + 1);
+            }
+            p.vt = ctx->vt; p.n_vt = kDecLayers;
+            p.a_ln_cs = m->kv_all.cs; p.a_ln_part = w.enc_st_b;
+            LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
+            if (launch_gemm_tc(p, r.s)) return 1;
+        }
+        ctx->pairs = B;
+        m->last_pairs = B;
+        return 0;
+    }
+    // fp32 SIMT cross-check path: explicit LayerNorm launches, the checkpoint's weights as they are
+    m->last_mem_pre_ln = false;
+    const int n_enc_dbg = (g_tc_variant >> 20) & 7;
+    for (int l = 0; l < (n_enc_dbg ? n_enc_dbg : kEncLayers); ++l) {
         const EncLayer& e = m->enc[l];
         {
             GemmParams p = gemm_base(T, 3 * kDModel, kDModel, cs(xin), kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, w.qk, 2 * kDModel);
@@ -572,31 +690,67 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
     // all 6 layers is one GEMM.
     if (run_linear(r, m->qpos_all, R, cs(w.qpos), kDModel, w.qp, kQpCols, false)) return 1;
 
-    for (int l = 0; l < kDecLayers; ++l) {
-        const DecLayer& d = m->dec[l];
-        CSplit16 q = cs(w.qp);      // layer 0: tgt = 0 (transformer.py:54), so q is the qpos projection alone
-        int ldq = kQpCols;
-        if (l > 0) {
-            if (run_linear(r, d.q, R, cs(w.t), kDModel, w.qb, kDModel, false, offset(cs(w.qp), (size_t)l * kDModel), kQpCols)) return 1;
-            q = cs(w.qb); ldq = kDModel;
+    if (m->gemm_path == 0) {
+        // Tensor-core path with deferred LayerNorms (see encode_impl): w.t = t + attention (norm2 deferred),
+        // w.t2 = t1 + FFN (norm3 deferred); dec_st_a = partial row statistics of w.t (norm2), dec_st_b of w.t2 (norm3).
+        for (int l = 0; l < kDecLayers; ++l) {
+            const DecLayer& d = m->dec[l];
+            const bool ln_in = l > 0;
+            CSplit16 q = cs(w.qp);      // layer 0: tgt = 0 (transformer.py:54), so q is the qpos projection alone
+            int ldq = kQpCols;
+            if (ln_in) {
+                if (run_linear_dln(r, d.q, R, cs(w.t2), kDModel, w.qb, kDModel, false, w.dec_st_b, nullptr,
+                                   offset(cs(w.qp), (size_t)l * kDModel), kQpCols)) return 1;
+                q = cs(w.qb); ldq = kDModel;
+            }
+            AttnParams a;
+            a.q = q; a.ldq = ldq;
+            a.k = offset(cs(ctx->k), (size_t)l * kDModel); a.ldk = kKCols;
+            a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
+            a.out = w.dao; a.ldo = kDModel;
+            a.nq = nq; a.npairs = npairs; a.pair0 = pair0;
+            if (run_attention(r, a)) return 1;
+            // transformer.py:196-197: t = t + out_proj(attn)   (norm2 deferred; t = norm3_{l-1}(t2), deferred, or 0)
+            if (run_linear_dln(r, d.o, R, cs(w.dao), kDModel, w.t, kDModel, false, nullptr, w.dec_st_a, ln_in ? cs(w.t2) : none, kDModel,
+                               ln_in ? w.dec_st_b : nullptr, ln_in ? m->dec[l - 1].ln3_g : nullptr, ln_in ? m->dec[l - 1].ln3_b : nullptr)) return 1;
+            // transformer.py:198-200: t2 = norm2(t) + linear2(relu(linear1(norm2(t))))   (norm3 deferred)
+            if (run_linear_dln(r, d.l1, R, cs(w.t), kDModel, w.dh, kFF, true, w.dec_st_a, nullptr)) return 1;
+            if (run_linear_dln(r, d.l2, R, cs(w.dh), kFF, w.t2, kDModel, false, nullptr, w.dec_st_b, cs(w.t), kDModel,
+                               w.dec_st_a, d.ln2_g, d.ln2_b)) return 1;
         }
-        AttnParams a;
-        a.q = q; a.ldq = ldq;
-        a.k = offset(cs(ctx->k), (size_t)l * kDModel); a.ldk = kKCols;
-        a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
-        a.out = w.dao; a.ldo = kDModel;
-        a.nq = nq; a.npairs = npairs; a.pair0 = pair0;
-        if (run_attention(r, a)) return 1;
-        // transformer.py:196-197: t = norm2(t + out_proj(attn))
-        if (run_linear(r, d.o, R, cs(w.dao), kDModel, w.t, kDModel, false, l > 0 ? cs(w.t) : none, kDModel, d.ln2_g, d.ln2_b, w.dln_tmp)) return 1;
-        // transformer.py:198-200: t = norm3(t + linear2(relu(linear1(t))))
-        if (run_linear(r, d.l1, R, cs(w.t), kDModel, w.dh, kFF, true)) return 1;
-        if (run_linear(r, d.l2, R, cs(w.dh), kFF, w.t, kDModel, false, cs(w.t), kDModel, d.ln3_g, d.ln3_b, w.dln_tmp)) return 1;
-    }
-    // transformer.py:110-111 decoder.norm on the last level; cotr_model.py:38-39 corr_embed on that level only.
-    {
-        LaunchScope scope(r, K_LAYERNORM, R, kDModel, 0);
-        if (launch_layernorm(cs(w.t), m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
+        // norm3 of the last layer, then transformer.py:110-111 decoder.norm, in one pass over the rows
+        {
+            const DecLayer& d = m->dec[kDecLayers - 1];
+            LaunchScope scope(r, K_LAYERNORM, R, kDModel, 0);
+            if (launch_layernorm_twice(cs(w.t2), d.ln3_g, d.ln3_b, m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
+        }
+    } else {
+        for (int l = 0; l < kDecLayers; ++l) {
+            const DecLayer& d = m->dec[l];
+            CSplit16 q = cs(w.qp);      // layer 0: tgt = 0 (transformer.py:54), so q is the qpos projection alone
+            int ldq = kQpCols;
+            if (l > 0) {
+                if (run_linear(r, d.q, R, cs(w.t), kDModel, w.qb, kDModel, false, offset(cs(w.qp), (size_t)l * kDModel), kQpCols)) return 1;
+                q = cs(w.qb); ldq = kDModel;
+            }
+            AttnParams a;
+            a.q = q; a.ldq = ldq;
+            a.k = offset(cs(ctx->k), (size_t)l * kDModel); a.ldk = kKCols;
+            a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
+            a.out = w.dao; a.ldo = kDModel;
+            a.nq = nq; a.npairs = npairs; a.pair0 = pair0;
+            if (run_attention(r, a)) return 1;
+            // transformer.py:196-197: t = norm2(t + out_proj(attn))
+            if (run_linear(r, d.o, R, cs(w.dao), kDModel, w.t, kDModel, false, l > 0 ? cs(w.t) : none, kDModel, d.ln2_g, d.ln2_b, w.dln_tmp)) return 1;
+            // transformer.py:198-200: t = norm3(t + linear2(relu(linear1(t))))
+            if (run_linear(r, d.l1, R, cs(w.t), kDModel, w.dh, kFF, true)) return 1;
+            if (run_linear(r, d.l2, R, cs(w.dh), kFF, w.t, kDModel, false, cs(w.t), kDModel, d.ln3_g, d.ln3_b, w.dln_tmp)) return 1;
+        }
+        // transformer.py:110-111 decoder.norm on the last level; cotr_model.py:38-39 corr_embed on that level only.
+        {
+            LaunchScope scope(r, K_LAYERNORM, R, kDModel, 0);
+            if (launch_layernorm(cs(w.t), m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
+        }
     }
     if (run_linear(r, m->head[0], R, cs(w.hs), kDModel, w.hd1, kDModel, true)) return 1;
     if (run_linear(r, m->head[1], R, cs(w.hd1), kDModel, w.hd2, kDModel, true)) return 1;
@@ -679,6 +833,17 @@ int build_model(cotr_model* m, const TensorMap& tm) {
         return make_linear(m, to_vec(w, (size_t)N * K), &bv, N, K, out);
     };
 
+    // same, for a layer whose input is a deferred LayerNorm `norm` (weight / bias in the checkpoint)
+    auto linear_ln_from = [&](const std::string& prefix, int N, int K, const std::string& norm, DevLinear* out) -> int {
+        const cotr_tensor* w = tm.get(prefix + ".weight", {N, K});
+        const cotr_tensor* b = tm.get(prefix + ".bias", {N});
+        const cotr_tensor* g = tm.get(norm + ".weight", {K});
+        const cotr_tensor* be = tm.get(norm + ".bias", {K});
+        if (!w || !b || !g || !be) return 1;
+        std::vector<float> bv = to_vec(b, N);
+        return make_linear_ln(m, to_vec(w, (size_t)N * K), &bv, N, K, g->data, be->data, out);
+    };
+
     // constant position-bias matrices, produced with the fp32 SIMT GEMM once per model
     struct PosBiasJob { std::vector<float> w_masked; std::vector<float> bias; int N; float** dst; };
     std::vector<PosBiasJob> jobs;
@@ -692,12 +857,25 @@ int build_model(cotr_model* m, const TensorMap& tm) {
         std::vector<float> wv = to_vec(w, 3 * DD), bv = to_vec(b, 3 * kDModel);
         for (size_t i = 0; i < DD; ++i) wv[i] *= qscale;
         for (int i = 0; i < kDModel; ++i) bv[i] *= qscale;
-        if (make_linear(m, wv, nullptr, 3 * kDModel, kDModel, &e.qkv)) return 1;
         std::vector<float> wm = wv;                               // value rows see x only, not x + pos
         std::fill(wm.begin() + 2 * DD, wm.end(), 0.f);
         jobs.push_back({wm, bv, 3 * kDModel, &e.add_qkv});
+        if (l == 0) {
+            if (make_linear(m, wv, nullptr, 3 * kDModel, kDModel, &e.qkv)) return 1;
+        } else {
+            // the layer input is norm2 of the previous layer, applied on the fly by this GEMM (tensor-core path)
+            const std::string prev = "transformer.encoder.layers." + std::to_string(l - 1) + ".norm2";
+            const cotr_tensor* g = tm.get(prev + ".weight", {kDModel});
+            const cotr_tensor* be = tm.get(prev + ".bias", {kDModel});
+            if (!g || !be) return 1;
+            std::vector<float> cb;
+            if (make_linear_ln(m, wv, nullptr, 3 * kDModel, kDModel, g->data, be->data, &e.qkv, &cb)) return 1;
+            std::vector<float> bv_tc = bv;
+            for (int i = 0; i < 3 * kDModel; ++i) bv_tc[i] += cb[i];
+            jobs.push_back({wm, bv_tc, 3 * kDModel, &e.add_qkv_tc});
+        }
         if (linear_from(p + ".self_attn.out_proj", kDModel, kDModel, &e.o)) return 1;
-        if (linear_from(p + ".linear1", kFF, kDModel, &e.l1)) return 1;
+        if (linear_ln_from(p + ".linear1", kFF, kDModel, p + ".norm1", &e.l1)) return 1;
         if (linear_from(p + ".linear2", kDModel, kFF, &e.l2)) return 1;
         if (upload_vec(m, tm, p + ".norm1.weight", kDModel, &e.ln1_g) || upload_vec(m, tm, p + ".norm1.bias", kDModel, &e.ln1_b) ||
             upload_vec(m, tm, p + ".norm2.weight", kDModel, &e.ln2_g) || upload_vec(m, tm, p + ".norm2.bias", kDModel, &e.ln2_b))
@@ -715,7 +893,15 @@ int build_model(cotr_model* m, const TensorMap& tm) {
         if (!w || !b) return 1;
         std::vector<float> wq = to_vec(w, DD);
         for (float& v : wq) v *= qscale;
-        if (make_linear(m, wq, nullptr, kDModel, kDModel, &d.q)) return 1;
+        if (l == 0) {
+            if (make_linear(m, wq, nullptr, kDModel, kDModel, &d.q)) return 1;       // (never run: tgt = 0 in layer 0)
+        } else {
+            const std::string prev = "transformer.decoder.layers." + std::to_string(l - 1) + ".norm3";
+            const cotr_tensor* g = tm.get(prev + ".weight", {kDModel});
+            const cotr_tensor* be = tm.get(prev + ".bias", {kDModel});
+            if (!g || !be) return 1;
+            if (make_linear_ln(m, wq, nullptr, kDModel, kDModel, g->data, be->data, &d.q)) return 1;
+        }
         memcpy(qp_w.data() + (size_t)l * DD, wq.data(), DD * sizeof(float));
         for (int i = 0; i < kDModel; ++i) qp_b[l * kDModel + i] = b->data[i] * qscale;
         // K rows then V rows of layer l
@@ -723,14 +909,24 @@ int build_model(cotr_model* m, const TensorMap& tm) {
         memcpy(kv_wm.data() + (size_t)l * 2 * DD, w->data + DD, DD * sizeof(float));   // only K sees pos
         memcpy(kv_b.data() + (size_t)l * 2 * kDModel, b->data + kDModel, 2 * kDModel * sizeof(float));
         if (linear_from(p + ".multihead_attn.out_proj", kDModel, kDModel, &d.o)) return 1;
-        if (linear_from(p + ".linear1", kFF, kDModel, &d.l1)) return 1;
+        if (linear_ln_from(p + ".linear1", kFF, kDModel, p + ".norm2", &d.l1)) return 1;
         if (linear_from(p + ".linear2", kDModel, kFF, &d.l2)) return 1;
         if (upload_vec(m, tm, p + ".norm2.weight", kDModel, &d.ln2_g) || upload_vec(m, tm, p + ".norm2.bias", kDModel, &d.ln2_b) ||
             upload_vec(m, tm, p + ".norm3.weight", kDModel, &d.ln3_g) || upload_vec(m, tm, p + ".norm3.bias", kDModel, &d.ln3_b))
             return 1;
         // decoder.layers.N.norm1.* exists in the checkpoint but transformer.py:185-201 never uses it.
     }
-    if (make_linear(m, kv_w, nullptr, kKvN, kDModel, &m->kv_all)) return 1;
+    {
+        const std::string last = "transformer.encoder.layers." + std::to_string(kEncLayers - 1) + ".norm2";
+        const cotr_tensor* g = tm.get(last + ".weight", {kDModel});
+        const cotr_tensor* be = tm.get(last + ".bias", {kDModel});
+        if (!g || !be) return 1;
+        std::vector<float> cb;
+        if (make_linear_ln(m, kv_w, nullptr, kKvN, kDModel, g->data, be->data, &m->kv_all, &cb)) return 1;
+        std::vector<float> kv_b_tc = kv_b;
+        for (int i = 0; i < kKvN; ++i) kv_b_tc[i] += cb[i];
+        jobs.push_back({kv_wm, kv_b_tc, kKvN, &m->add_kv_tc});
+    }
     jobs.push_back({kv_wm, kv_b, kKvN, &m->add_kv});
     if (make_linear(m, qp_w, &qp_b, kQpCols, kDModel, &m->qpos_all)) return 1;
     if (upload_vec(m, tm, "transformer.decoder.norm.weight", kDModel, &m->dec_norm_g) ||
@@ -759,6 +955,7 @@ int build_model(cotr_model* m, const TensorMap& tm) {
         cudaFree(bd);
     }
     ws_free(&pos16);
+    if (!m->enc[0].add_qkv_tc) m->enc[0].add_qkv_tc = m->enc[0].add_qkv;     // layer 0 reads the un-normalised input projection
     return 0;
 }
 
@@ -811,9 +1008,11 @@ void cotr_destroy(cotr_model* m) {
     for (void* p : m->allocs) cudaFree(p);
     Workspace& w = m->ws;
     Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh,
-                       &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2};
+                       &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2, &w.t2};
     for (Split16* b : bufs) ws_free(b);
-    float** fbufs[] = {&w.ln_tmp, &w.dln_tmp, &w.img_stage, &w.q_stage, &w.pred_stage};
+    float** fbufs[] = {&w.ln_tmp, &w.dln_tmp, &w.img_stage, &w.q_stage, &w.pred_stage,
+                       reinterpret_cast<float**>(&w.enc_st_a), reinterpret_cast<float**>(&w.enc_st_b),
+                       reinterpret_cast<float**>(&w.dec_st_a), reinterpret_cast<float**>(&w.dec_st_b)};
     for (float** b : fbufs) ws_free_f32(b);
     if (m->host_stream) cudaStreamDestroy(m->host_stream);
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
@@ -993,6 +1192,11 @@ int cotr_dense_postprocess(cotr_model* m, const float* pred_dev, int n, float* o
     return dense_post_launch(pred_dev, out_dev, n, (cudaStream_t)cuda_stream);
 }
 
+int cotr_rasterize_triangles(int device, const float* tris_dev, int n_tri, int H, int W, float* out_dev, void* cuda_stream) {
+    COTR_CHECK_CUDA(cudaSetDevice(device));
+    return rasterize_triangles_launch(tris_dev, n_tri, H, W, out_dev, (cudaStream_t)cuda_stream);
+}
+
 int cotr_set_graph_mode(cotr_model* m, int enabled) {
     COTR_CHECK(m != nullptr, "cotr_set_graph_mode: null model");
     m->graph_mode = enabled != 0;
@@ -1033,6 +1237,13 @@ int cotr_profile_end(cotr_model* m, cotr_launch_record* out, int max_records) {
     return -n - 1;     // see header: success is encoded as -(count + 1)
 }
 
+namespace {
+struct TmpSplitDbg {
+    Split16 t = kNoSplit;
+    ~TmpSplitDbg() { ws_free(&t); }
+};
+}  // namespace
+
 int64_t cotr_debug_read(cotr_model* m, const char* name, float* out_host, int64_t max_elems) {
     if (!m || !name || !out_host) return -1;
     cudaSetDevice(m->device);
@@ -1044,8 +1255,28 @@ int64_t cotr_debug_read(cotr_model* m, const char* name, float* out_host, int64_
     if (s == "feat") { src = cs(m->last_feat); n = (int64_t)m->last_pairs * 2 * 16 * 16 * 1024; }
     else if (s == "src") { src = cs(m->ws.src); n = (int64_t)m->last_pairs * kTokens * kDModel; }
     else if (s == "mem") { src = cs(m->last_mem); n = (int64_t)m->last_pairs * kTokens * kDModel; }
+    TmpSplitDbg mem_ln;
+    if (s == "mem" && m->last_mem_pre_ln && src.hi && n > 0) {
+        // tensor-core path: the encoder output exists only before its last (deferred) LayerNorm - apply it here
+        const EncLayer& e = m->enc[kEncLayers - 1];
+        if (ws_alloc(&mem_ln.t, (size_t)n) || launch_layernorm(src, e.ln2_g, e.ln2_b, mem_ln.t, (int)(n / kDModel), 0) ||
+            cudaDeviceSynchronize() != cudaSuccess)
+            return -1;
+        src = cs(mem_ln.t);
+    }
     else if (s == "hs") { src = cs(m->ws.hs); n = (int64_t)m->last_rows * kDModel; }
     else if (s == "pos") { src_f32 = m->pos; n = (int64_t)kTokens * kDModel; }
+    // bring-up: raw workspace buffers of the last forward (tokens = pairs * 512, rows = the decoder rows of the last chunk)
+    else if (s == "ws.xa") { src = cs(m->ws.xa); n = (int64_t)m->last_pairs * kTokens * kDModel; }
+    else if (s == "ws.xb") { src = cs(m->ws.xb); n = (int64_t)m->last_pairs * kTokens * kDModel; }
+    else if (s == "ws.ao") { src = cs(m->ws.ao); n = (int64_t)m->last_pairs * kTokens * kDModel; }
+    else if (s == "ws.qk") { src = cs(m->ws.qk); n = (int64_t)m->last_pairs * kTokens * 2 * kDModel; }
+    else if (s == "ws.ffh") { src = cs(m->ws.ffh); n = (int64_t)m->last_pairs * kTokens * kFF; }
+    else if (s == "ws.t") { src = cs(m->ws.t); n = (int64_t)m->last_rows * kDModel; }
+    else if (s == "ws.t2") { src = cs(m->ws.t2); n = (int64_t)m->last_rows * kDModel; }
+    else if (s == "ws.dao") { src = cs(m->ws.dao); n = (int64_t)m->last_rows * kDModel; }
+    else if (s == "ws.st_a") { src_f32 = reinterpret_cast<const float*>(m->ws.enc_st_a); n = (int64_t)m->last_pairs * kTokens * 32; }
+    else if (s == "ws.st_b") { src_f32 = reinterpret_cast<const float*>(m->ws.enc_st_b); n = (int64_t)m->last_pairs * kTokens * 32; }
     if ((!src.hi && !src_f32) || n <= 0 || n > max_elems) return -1;
     float* tmp = nullptr;
     if (!src_f32) {
@@ -1092,7 +1323,7 @@ struct TmpSplit {
 
 int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float* w_host, const float* bias_dev,
                    const float* addmat_dev, const float* residual_dev, const float* ln_gamma_dev,
-                   const float* ln_beta_dev, float* out_dev) {
+                   const float* ln_beta_dev, float* out_dev, float* part_out_dev) {
     COTR_CHECK(d && A_dev && w_host && out_dev, "cotr_test_gemm: null argument");
     COTR_CHECK(d->ldc == d->N, "cotr_test_gemm: ldc must equal N");
     GemmParams p;
@@ -1103,7 +1334,9 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
     p.KH = d->KH; p.KW = d->KW; p.stride = d->stride; p.pad = d->pad;
     p.bias = bias_dev; p.addmat = addmat_dev; p.add_period = d->add_period > 0 ? d->add_period : 1; p.ld_add = d->ld_add;
     p.ldr = d->ldr; p.relu = d->relu;
-    p.ln_gamma = ln_gamma_dev; p.ln_beta = ln_beta_dev;
+    const bool dln = d->a_ln != 0 || d->res_ln != 0;
+    COTR_CHECK(!dln || (d->path == 0 && ln_gamma_dev && ln_beta_dev), "cotr_test_gemm: deferred LayerNorm needs path 0 and gamma / beta");
+    if (!dln) { p.ln_gamma = ln_gamma_dev; p.ln_beta = ln_beta_dev; }
     p.ldc = d->ldc;
     TmpSplit a16, res16, out16;
     if (d->a_mode == A_STEM_NCHW) {
@@ -1126,6 +1359,49 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
     const size_t wn = (size_t)d->N * d->K;
     COTR_CHECK_CUDA(cudaMalloc((void**)&wd, wn * sizeof(float)));
     COTR_CHECK_CUDA(cudaMemcpy(wd, w_host, wn * sizeof(float), cudaMemcpyHostToDevice));
+    // deferred LayerNorm of A: the packed weights carry gamma, column sums and beta W^T + bias go to the epilogue
+    std::vector<float> w_fold;
+    float *cs_dev = nullptr, *cb_dev = nullptr;
+    float2 *stats_dev = nullptr, *res_stats_dev = nullptr;
+    if (d->a_ln) {
+        COTR_CHECK(d->K == 256 && d->a_mode == A_ROWMAJOR, "cotr_test_gemm: a_ln needs K = 256, row-major A");
+        std::vector<float> g(d->K), be(d->K), bias_h(d->N, 0.f), cs(d->N), cb(d->N);
+        COTR_CHECK_CUDA(cudaMemcpy(g.data(), ln_gamma_dev, d->K * sizeof(float), cudaMemcpyDeviceToHost));
+        COTR_CHECK_CUDA(cudaMemcpy(be.data(), ln_beta_dev, d->K * sizeof(float), cudaMemcpyDeviceToHost));
+        if (bias_dev) COTR_CHECK_CUDA(cudaMemcpy(bias_h.data(), bias_dev, d->N * sizeof(float), cudaMemcpyDeviceToHost));
+        w_fold.resize(wn);
+        for (int n = 0; n < d->N; ++n) {
+            double sum = 0.0, c = bias_h[n];
+            for (int k = 0; k < d->K; ++k) {
+                const float v = w_host[(size_t)n * d->K + k] * g[k];
+                w_fold[(size_t)n * d->K + k] = v;
+                sum += v;
+                c += (double)w_host[(size_t)n * d->K + k] * be[k];
+            }
+            cs[n] = (float)sum; cb[n] = (float)c;
+        }
+        COTR_CHECK_CUDA(cudaMalloc((void**)&cs_dev, d->N * sizeof(float)));
+        COTR_CHECK_CUDA(cudaMalloc((void**)&cb_dev, d->N * sizeof(float)));
+        COTR_CHECK_CUDA(cudaMemcpy(cs_dev, cs.data(), d->N * sizeof(float), cudaMemcpyHostToDevice));
+        COTR_CHECK_CUDA(cudaMemcpy(cb_dev, cb.data(), d->N * sizeof(float), cudaMemcpyHostToDevice));
+        p.a_ln_cs = cs_dev; p.bias = cb_dev;
+        w_host = w_fold.data();
+    }
+    if (d->a_ln) {
+        COTR_CHECK_CUDA(cudaMalloc((void**)&stats_dev, (size_t)d->M * 16 * sizeof(float2)));
+        if (launch_ln_partials(p.a, stats_dev, d->M, 0)) return 1;
+        p.a_ln_part = stats_dev;
+    }
+    if (d->res_ln) {
+        COTR_CHECK(residual_dev && d->ldr == 256 && d->N == 256, "cotr_test_gemm: res_ln needs a [M,256] residual");
+        COTR_CHECK_CUDA(cudaMalloc((void**)&res_stats_dev, (size_t)d->M * 16 * sizeof(float2)));
+        if (launch_ln_partials(p.res, res_stats_dev, d->M, 0)) return 1;
+        p.res_ln_part = res_stats_dev; p.res_ln_gamma = ln_gamma_dev; p.res_ln_beta = ln_beta_dev;
+    }
+    if (d->emit_part) {
+        COTR_CHECK(d->path == 0 && part_out_dev != nullptr && d->N == 256, "cotr_test_gemm: emit_part needs path 0, N = 256 and an output buffer");
+        p.ln_part_out = reinterpret_cast<float2*>(part_out_dev);
+    }
     const size_t tcb = tc_weight_bytes(d->N, d->K);
     std::vector<uint8_t> img(tcb);
     p.acc_scale = tc_pack_weight(w_host, d->N, d->K, img.data());
@@ -1151,6 +1427,10 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
     cudaFree(wd);
     cudaFree(wtc);
     if (scratch) cudaFree(scratch);
+    if (cs_dev) cudaFree(cs_dev);
+    if (cb_dev) cudaFree(cb_dev);
+    if (stats_dev) cudaFree(stats_dev);
+    if (res_stats_dev) cudaFree(res_stats_dev);
     if (rc) return rc;
     COTR_CHECK(e == cudaSuccess, "cotr_test_gemm: kernel failed: %s", cudaGetErrorString(e));
     return 0;

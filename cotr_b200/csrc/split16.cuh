@@ -30,10 +30,15 @@ __device__ __forceinline__ float2 join_f16x2(uint32_t hi, uint32_t lo) {
 }
 __device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 
-// 8 consecutive elements (16 bytes per plane) -> 8 floats
+// 8 consecutive elements (16 bytes per plane) -> 8 floats.
+// Activations are read with ld.global.cg, never through the non-coherent path (__ldg / ld.global.nc): under
+// programmatic dependent launch a kernel is resident while its predecessor still writes these buffers, so they are not
+// read-only for the kernel's lifetime, which .nc requires - measured: an SM's L1 kept row statistics of the PREVIOUS
+// forward across the launches in between and a .nc load after griddepcontrol.wait returned them
+// (profiles/r02_deferred_layernorm.md).  Constants (weights, biases, gamma / beta, tables) keep __ldg.
 __device__ __forceinline__ void load8_split(const CSplit16& t, size_t off, float (&v)[8]) {
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(t.hi + off));
-    const uint4 l = __ldg(reinterpret_cast<const uint4*>(t.lo + off));
+    const uint4 h = __ldcg(reinterpret_cast<const uint4*>(t.hi + off));
+    const uint4 l = __ldcg(reinterpret_cast<const uint4*>(t.lo + off));
     float2 f;
     f = join_f16x2(h.x, l.x); v[0] = f.x; v[1] = f.y;
     f = join_f16x2(h.y, l.y); v[2] = f.x; v[3] = f.y;

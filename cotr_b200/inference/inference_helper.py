@@ -232,24 +232,18 @@ def cotr_corr_base(model, img_a, img_b, queries_a):
 
 
 def triangulate_corr(corr, from_shape, to_shape):
-    """Densify sparse correspondences: Delaunay over the source points + barycentric interpolation of the targets.
-
-    The reference renders the triangles with OpenGL through vispy (:293-308) and falls back to `None` when vispy is
-    missing.  This is a CPU rasteriser with the same output contract: (H_from, W_from, 2) float32 target pixel
-    coordinates, zeros outside the triangulated hull.  Visual densification is outside the accelerated hot path.
-    """
+    """Densify sparse correspondences (:293-308): Delaunay triangulation of the source points on the host (scipy, as
+    in the reference), then barycentric interpolation of the target coordinates over every triangle.  The reference
+    renders the triangles with OpenGL through vispy (and is `None` without vispy); here the rendering is a CUDA
+    rasteriser behind the C ABI (cotr_rasterize_triangles): pixel (x, y) is sampled at its centre (x + 0.5, y + 0.5)
+    like GL does.  Returns (H_from, W_from, 2) float32 target pixel coordinates, zeros outside the triangulated hull."""
     from scipy.spatial import Delaunay
+    from .. import capi
+    if not torch.cuda.is_available():
+        raise RuntimeError("triangulate_corr renders on the GPU (cotr_rasterize_triangles); no CUDA device is visible")
     corr = np.asarray(corr, dtype=np.float64)
     h, w = from_shape[:2]
     tri = Delaunay(corr[:, :2])
-    ys, xs = np.mgrid[0:h, 0:w]
-    pix = np.stack([xs.ravel() + 0.5, ys.ravel() + 0.5], axis=1)
-    simplex = tri.find_simplex(pix)
-    out = np.zeros((h * w, 2), dtype=np.float32)
-    ok = simplex >= 0
-    T = tri.transform[simplex[ok]]
-    bary2 = np.einsum('nij,nj->ni', T[:, :2], pix[ok] - T[:, 2])
-    bary = np.concatenate([bary2, 1 - bary2.sum(axis=1, keepdims=True)], axis=1)
-    verts = tri.simplices[simplex[ok]]
-    out[ok] = np.einsum('nk,nkc->nc', bary, corr[verts, 2:4]).astype(np.float32)
-    return out.reshape(h, w, 2)
+    verts = corr[tri.simplices].astype(np.float32)                   # (n_tri, 3, [x_from, y_from, x_to, y_to])
+    out = capi.rasterize_triangles(torch.from_numpy(np.ascontiguousarray(verts)).cuda(), h, w)
+    return out.cpu().numpy()

@@ -1,11 +1,25 @@
-"""Multi-GPU data parallelism over independent image pairs.
+"""Multi-GPU data parallelism over independent image pairs / contexts.
 
-One process per GPU (torchrun).  Pairs / contexts are independent, so the only exchange is the gather of the
-(B,Q,2) fp32 predictions - 8 KB per 1024 queries.  Works with the `nccl` backend on CUDA tensors and with `gloo` on
-CPU tensors (used by the CPU tests).
+One process per GPU (torchrun).  Pairs (and the zoom-in engines' contexts) are independent, so the only exchange is
+the gather of the (B,Q,2) fp32 predictions - 8 KB per 1024 queries.  Works with the `nccl` backend on CUDA tensors and
+with `gloo` on CPU tensors (used by the CPU tests).
+
+Two entry points:
+  * `forward_sharded(model, img, queries)`: BASELINE.json configs[3] - one batch of independent pairs, each rank runs
+    its contiguous block, everybody receives all predictions;
+  * `ShardedCOTR(model)`: a drop-in for the model object the engines drive (`SparseEngine(ShardedCOTR(model), ...)`,
+    BASELINE.json configs[4], reference call site demo_reconstruction.py:44-49).  The host scheduler runs replicated
+    (SPMD): every rank executes the same engine code with the same seeds, every model call is split over the ranks
+    (contexts contiguously; the single-context dense pass of cotr_flow over its 131 072 queries) and all-gathered, so
+    every rank sees identical predictions and takes identical decisions.  Task state therefore needs no broadcast,
+    and rank 0's return value is the job's result.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
+from torch import nn
+
+MIN_QUERIES_TO_SPLIT = 4096      # below this a single context is not worth splitting over its queries
 
 
 def pair_range(n_pairs, rank, world):
@@ -15,26 +29,35 @@ def pair_range(n_pairs, rank, world):
     return start, start + base + (1 if rank < extra else 0)
 
 
-def gather_predictions(local_pred, n_pairs, group=None):
-    """All-gather per-rank (b_r,Q,2) predictions into the full (n_pairs,Q,2) tensor on every rank, in pair order."""
-    if not (dist.is_available() and dist.is_initialized()):
-        return local_pred
+def _active(group=None):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def _gather_blocks(local, total, dim, group=None):
+    """All-gather per-rank blocks of `total` items split contiguously (pair_range) along `dim`, in order."""
+    if not _active(group):
+        return local
     world = dist.get_world_size(group)
-    q = local_pred.shape[1]
-    counts = [pair_range(n_pairs, r, world) for r in range(world)]
+    counts = [pair_range(total, r, world) for r in range(world)]
     widest = max(e - s for s, e in counts)
-    padded = torch.zeros((widest, q, 2), dtype=local_pred.dtype, device=local_pred.device)
-    padded[: local_pred.shape[0]] = local_pred
-    out = torch.empty((world * widest, q, 2), dtype=local_pred.dtype, device=local_pred.device)
+    local = local.movedim(dim, 0).contiguous()
+    padded = local.new_zeros((widest,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    out = local.new_empty((world * widest,) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(out, padded, group=group)
     parts = [out[r * widest: r * widest + (e - s)] for r, (s, e) in enumerate(counts)]
-    return torch.cat(parts, dim=0)
+    return torch.cat(parts, dim=0).movedim(0, dim).contiguous()
+
+
+def gather_predictions(local_pred, n_pairs, group=None):
+    """All-gather per-rank (b_r,Q,2) predictions into the full (n_pairs,Q,2) tensor on every rank, in pair order."""
+    return _gather_blocks(local_pred, n_pairs, 0, group)
 
 
 def forward_sharded(model, img, queries, group=None):
     """BASELINE.json configs[3]: every rank holds the full (B,3,256,512) / (B,Q,2) batch description, runs its own
     block of pairs through `model` and receives everybody's predictions."""
-    if not (dist.is_available() and dist.is_initialized()):
+    if not _active(group):
         return model(img, queries)['pred_corrs']
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     s, e = pair_range(img.shape[0], rank, world)
@@ -43,3 +66,72 @@ def forward_sharded(model, img, queries, group=None):
     else:
         local = queries.new_zeros((0, queries.shape[1], 2))
     return gather_predictions(local, img.shape[0], group)
+
+
+class LazyCanvases:
+    """What `ShardedCOTR.preprocess_canvases` returns: the recipe of n network canvases (two uint8 device images and
+    n crop rectangles), materialised per rank for its own block only when the forward is issued."""
+
+    def __init__(self, img_from, img_to, rects):
+        self.img_from, self.img_to = img_from, img_to
+        self.rects = np.ascontiguousarray(rects, dtype=np.int32)
+        self.shape = (self.rects.shape[0], 3, 256, 512)
+
+    def to(self, *a, **k):
+        return self
+
+    def __len__(self):
+        return self.shape[0]
+
+
+class ShardedCOTR(nn.Module):
+    """The model object of the engines, with every call split over the ranks of `group` (see the module docstring)."""
+
+    def __init__(self, model, group=None):
+        super().__init__()
+        self.model = model
+        self.group = group
+
+    @property
+    def supports_device_preprocess(self):
+        return getattr(self.model, 'supports_device_preprocess', False)
+
+    def preprocess_canvases(self, img_from_u8, img_to_u8, rects):
+        if not _active(self.group):
+            return self.model.preprocess_canvases(img_from_u8, img_to_u8, rects)
+        return LazyCanvases(img_from_u8, img_to_u8, rects)
+
+    def _local_canvases(self, samples, s, e):
+        if isinstance(samples, LazyCanvases):
+            return self.model.preprocess_canvases(samples.img_from, samples.img_to, samples.rects[s:e])
+        return samples[s:e]
+
+    @torch.no_grad()
+    def forward(self, samples, queries):
+        if not _active(self.group):
+            if isinstance(samples, LazyCanvases):
+                samples = self._local_canvases(samples, 0, samples.shape[0])
+            return self.model(samples, queries)
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        B, Q = int(queries.shape[0]), int(queries.shape[1])
+        if B == 1 and Q >= MIN_QUERIES_TO_SPLIT and not isinstance(samples, LazyCanvases):
+            # one context, many queries (cotr_flow's dense pass): every rank encodes the (cheap) context itself and
+            # decodes its slice of the queries - no broadcast of the 6 MB K/V cache
+            s, e = pair_range(Q, rank, world)
+            local = self.model(samples, queries[:, s:e].contiguous())['pred_corrs']
+            return {'pred_corrs': _gather_blocks(local, Q, 1, self.group)}
+        s, e = pair_range(B, rank, world)
+        if e > s:
+            local = self.model(self._local_canvases(samples, s, e), queries[s:e])['pred_corrs']
+        else:
+            dev = next(self.model.parameters()).device
+            local = torch.zeros((0, Q, 2), dtype=torch.float32, device=dev)
+        return {'pred_corrs': gather_predictions(local, B, self.group)}
+
+    # The remaining extensions of cotr_b200.models.COTR (dense_postprocess, encode_context, decode) run replicated:
+    # identical on every rank, no exchange.  They exist on the wrapper exactly when the wrapped model has them.
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(super().__getattr__('model'), name)

@@ -98,6 +98,13 @@ int cotr_preprocess(cotr_model* m, const uint8_t* img_from_dev, int h_from, int 
  * `corr` array before it is split into its two halves (grid_sample: bilinear, zero padding, align_corners = False). */
 int cotr_dense_postprocess(cotr_model* m, const float* pred_dev, int n, float* out_dev, void* cuda_stream);
 
+/* The rendering half of triangulate_corr (COTR/inference/inference_helper.py:293-308; the reference rasterises the
+ * Delaunay triangles of the source points with OpenGL through vispy, vertex colour = target coordinates).
+ * tris_dev: n_tri x 3 vertices x 4 fp32 [x, y, u, v] (DEVICE; x, y in pixels of the H x W source image, u, v the values
+ * to interpolate); out_dev: H x W x 2 fp32 (DEVICE) = barycentric interpolation of (u, v) at every pixel centre
+ * (x + 0.5, y + 0.5) covered by a triangle (top-left fill rule), zero elsewhere.  `device` is the CUDA device index. */
+int cotr_rasterize_triangles(int device, const float* tris_dev, int n_tri, int H, int W, float* out_dev, void* cuda_stream);
+
 /* cotr_forward / cotr_forward_host replay a CUDA graph per (B,Q) shape (captured on the second call with that shape;
  * inputs / outputs pass through internal staging buffers so the graph's addresses stay fixed).  0 disables it. */
 int cotr_set_graph_mode(cotr_model* m, int enabled);
@@ -140,6 +147,11 @@ typedef struct cotr_test_gemm_desc {
     int32_t H, W, C, OH, OW, KH, KW, stride, pad;   /* convolution geometry for a_mode 1 / 2                  */
     int32_t relu;
     int32_t add_period, ld_add, ldr, ldc;
+    int32_t a_ln;                 /* 1: A holds PRE-LayerNorm rows (K = 256); ln_gamma / ln_beta are the norm of A,
+                                     applied on the fly (deferred LayerNorm, tcgen05 path only) instead of an output norm */
+    int32_t res_ln;               /* 1: the residual (ldr = N = 256) is a deferred LayerNorm too, same gamma / beta   */
+    int32_t emit_part;            /* 1: also write the [M][16] (mean, M2) partial row statistics of the output (N = 256) */
+    int32_t reserved;
     int64_t a_elems;              /* element count of the A activation tensor (a_mode 0 / 1 / 3)                 */
 } cotr_test_gemm_desc;
 /* out = epilogue(A * W^T): A/bias/addmat/residual/ln_* /out are fp32 DEVICE pointers (may be NULL where optional) -
@@ -147,7 +159,7 @@ typedef struct cotr_test_gemm_desc {
  * [N,K] matrix (packed for the tensor-core path internally). */
 int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float* w_host, const float* bias_dev,
                    const float* addmat_dev, const float* residual_dev, const float* ln_gamma_dev,
-                   const float* ln_beta_dev, float* out_dev);
+                   const float* ln_beta_dev, float* out_dev, float* part_out_dev /* [M][16][2] or NULL */);
 /* out[(p*nq+i), h*32+d] = softmax(q k^T) v per head; q (npairs*nq,256), k/v (npairs*512,256), all DEVICE, ld 256. */
 int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const float* v_dev, float* out_dev,
                         int nq, int npairs);

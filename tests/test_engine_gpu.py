@@ -182,3 +182,26 @@ def test_context_reuse_in_corr_base(models):
     got = cotr_corr_base(native, img_a, img_b, q.copy())
     ref = cotr_corr_base(oracle, img_a, img_b, q.copy())
     assert np.abs(got - ref).max() < 0.6          # pixels: 1e-3 * 2 * 256 = 0.5 px per axis at full scale
+
+
+def test_triangulate_corr_cuda_rasteriser_matches_oracle(built_lib):
+    """cotr_rasterize_triangles (the GL rendering of inference_helper.py:293-308 as a CUDA kernel) against the CPU
+    restatement: same Delaunay triangles (scipy on both sides), barycentric interpolation at every pixel centre.
+    Coverage may differ only for pixel centres that lie (numerically) ON a hull edge; values are piecewise linear and
+    continuous across interior edges, so they agree wherever both sides are inside."""
+    from cotr_b200.inference.inference_helper import triangulate_corr
+    from oracle import triangulate_oracle
+    rs = np.random.RandomState(12)
+    for (h, w, n) in ((240, 320, 40), (783, 1064, 300), (64, 64, 3)):
+        src = np.stack([rs.uniform(2, w - 2, n), rs.uniform(2, h - 2, n)], axis=1)
+        dst = src * np.array([0.9, 1.1]) + rs.uniform(-20, 20, (n, 2))
+        corr = np.concatenate([src, dst], axis=1)
+        got = triangulate_corr(corr, (h, w, 3), (h + 10, w + 10, 3))
+        ref, inside = triangulate_oracle.triangulate_corr(corr, (h, w, 3), (h + 10, w + 10, 3))
+        assert got.shape == ref.shape == (h, w, 2) and got.dtype == np.float32
+        got_inside = (got != 0).any(axis=2)
+        assert (got_inside != inside).mean() < 2e-4                      # hull-edge pixel centres only
+        both = got_inside & inside
+        assert both.mean() > 0.2
+        assert np.abs(got[both] - ref[both]).max() < 2e-3                # pixels of the target image (coords up to ~1e3)
+        assert (got[~got_inside] == 0).all()

@@ -56,6 +56,57 @@ def test_gemm_residual_layernorm_epilogue(capi, path):
     assert _rel(out, ref) < REL[path]
 
 
+@pytest.mark.parametrize("M,N,mean", [(512, 768, 0.0), (1024, 1024, 3.0), (300, 256, -1.5), (4100, 3072, 0.5), (9000, 1024, 0.0)])
+def test_gemm_deferred_layernorm_on_a(capi, M, N, mean):
+    """GemmParams::a_ln_cs: A holds pre-LayerNorm rows, the GEMM consumes LN(A) without materialising it (weights carry
+    gamma, two spare warps compute the row statistics from the staged tile, the epilogue finishes the algebra).
+    Rows with a mean of several sigma stress the  x W'^T - mean colsum(W')  cancellation."""
+    g = _gen(M + N)
+    K = 256
+    A = (torch.randn(M, K, generator=g) * (0.5 + torch.rand(M, 1, generator=g) * 4) + mean).cuda()
+    W = torch.randn(N, K, generator=g) * 0.08
+    bias = torch.randn(N, generator=g).cuda()
+    gam = (1 + 0.2 * torch.randn(K, generator=g)).cuda()
+    bet = (0.2 * torch.randn(K, generator=g)).cuda()
+    ref = (F.layer_norm(A.double(), (K,), gam.double(), bet.double(), 1e-5) @ W.cuda().double().t() + bias.double()).relu()
+    out = capi.test_gemm(TC, A, W.numpy(), bias=bias, relu=True, ln=(gam, bet), a_ln=True)
+    assert _rel(out, ref) < 4e-6
+
+
+@pytest.mark.parametrize("M,K", [(512, 1024), (1000, 256), (4224, 256)])
+def test_gemm_emits_partial_row_statistics(capi, M, K):
+    """GemmParams::ln_part_out: a GEMM whose 256-wide output rows will be layer-normalised later leaves, per row and
+    16-column chunk, the chunk's (mean, M2) - what the deferred-LayerNorm consumers merge into (mean, rstd)."""
+    g = _gen(M + K + 1)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = torch.randn(256, K, generator=g) * 0.1
+    bias = (torch.randn(256, generator=g) * 2).cuda()
+    part = torch.zeros(M, 16, 2, device="cuda")
+    out = capi.test_gemm(TC, A, W.numpy(), bias=bias, part_out=part)
+    chunks = out.double().view(M, 16, 16)
+    mean = chunks.mean(-1)
+    m2 = ((chunks - mean[..., None]) ** 2).sum(-1)
+    assert (part[..., 0].double() - mean).abs().max().item() < 1e-5
+    assert ((part[..., 1].double() - m2).abs() / m2.clamp_min(1e-3)).max().item() < 1e-4
+
+
+@pytest.mark.parametrize("M,K", [(512, 256), (1024, 1024), (512, 1024), (200, 256)])
+def test_gemm_deferred_layernorm_residual(capi, M, K):
+    """GemmParams::res_ln_part: the residual operand is a deferred LayerNorm of stored pre-norm rows, normalised on the
+    fly from the partial row statistics ((512, 1024) is the encoder's FFN2: split-K over a cluster of 4)."""
+    g = _gen(M + K)
+    N = 256
+    A = torch.randn(M, K, generator=g).cuda()
+    W = torch.randn(N, K, generator=g) * 0.05
+    bias = torch.randn(N, generator=g).cuda()
+    res = (torch.randn(M, N, generator=g) * 2 + 0.7).cuda()
+    gam = (1 + 0.2 * torch.randn(N, generator=g)).cuda()
+    bet = (0.2 * torch.randn(N, generator=g)).cuda()
+    ref = A.double() @ W.cuda().double().t() + bias.double() + F.layer_norm(res.double(), (N,), gam.double(), bet.double(), 1e-5)
+    out = capi.test_gemm(TC, A, W.numpy(), bias=bias, residual=res, ln=(gam, bet), res_ln=True)
+    assert _rel(out, ref) < 2.5e-6
+
+
 @pytest.mark.parametrize("path", [TC, SIMT])
 def test_gemm_periodic_add_matrix(capi, path):
     """The constant (pos W^T + b) matrices are added with a 512-row period (one period per image pair)."""

