@@ -45,6 +45,10 @@ _PROTOTYPES = {
     "cotr_preprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_dense_postprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_flow_tile_merge": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 6 +
+                             [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "cotr_group_tasks": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_rasterize_triangles": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_set_graph_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cotr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
@@ -71,7 +75,12 @@ def lib():
                                "(cotr_b200 has no CPU / PyTorch fallback by design)")
         handle = ctypes.CDLL(LIB_PATH)
         for name, (restype, argtypes) in _PROTOTYPES.items():
-            fn = getattr(handle, name)
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                if os.environ.get("COTR_B200_ALLOW_OLD_LIB"):       # tools/ab_libs.py: A/B against a build of an older revision
+                    continue
+                raise
             fn.restype = restype
             fn.argtypes = argtypes
         _lib = handle
@@ -189,6 +198,15 @@ class NativeModel:
         check(lib().cotr_dense_postprocess(self.handle, _ptr(pred_dev), n, _ptr(out), self._stream()), "cotr_dense_postprocess")
         return out
 
+    def flow_tile_merge(self, tile, affine, patch, flow, conf, first):
+        """One 256 x 256 x 3 tile answer (a view into dense_postprocess' output) -> affine, Pillow-exact float resize to
+        the patch size, confidence merge into the (oh,ow,2) / (oh,ow) device canvases (cotr_flow_tile_merge)."""
+        assert tile.is_cuda and tile.dtype == torch.float32 and tile.shape == (256, 256, 3) and tile.stride(2) == 1 and tile.stride(1) == 3
+        aff = np.ascontiguousarray(affine, dtype=np.float64).reshape(6)
+        check(lib().cotr_flow_tile_merge(self.handle, _ptr(tile), int(tile.stride(0)), ctypes.c_void_p(aff.ctypes.data),
+                                         int(patch.x), int(patch.y), int(patch.w), int(patch.h), int(patch.ow), int(patch.oh),
+                                         _ptr(flow), _ptr(conf), int(bool(first)), self._stream()), "cotr_flow_tile_merge")
+
     def set_graph_mode(self, enabled):
         check(lib().cotr_set_graph_mode(self.handle, int(bool(enabled))), "cotr_set_graph_mode")
 
@@ -228,6 +246,22 @@ class NativeModel:
             self.close()
         except Exception:
             pass
+
+
+def group_tasks(pts, boxes, batch_size, max_load, device):
+    """(n,4) end points + (n,8) pilot boxes (float64 numpy, list order) -> (squad (n,), rank (n,), n_squads): the device
+    version of FasterSparseEngine's squad formation (cotr_group_tasks)."""
+    n = int(pts.shape[0])
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    p = torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64)).to(dev)
+    b = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.float64)).to(dev)
+    out = torch.empty(2 * n + 1, dtype=torch.int32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+    check(lib().cotr_group_tasks(idx, _ptr(p), _ptr(b), n, int(batch_size), int(max_load), _ptr(out), ctypes.c_void_p(out.data_ptr() + 4 * n),
+                                 ctypes.c_void_p(out.data_ptr() + 8 * n), stream), "cotr_group_tasks")
+    host = out.cpu().numpy()
+    return host[:n], host[n:2 * n], int(host[2 * n])
 
 
 def rasterize_triangles(tris, H, W):

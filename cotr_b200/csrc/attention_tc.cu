@@ -70,12 +70,15 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
     uint64_t* o_full = bars + 3;
     uint64_t* p_full = bars + 4;     // [2]
     uint64_t* p_empty = bars + 6;    // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* dep_ready = bars + 8;  // dataflow mode (common.cuh LaunchSync): the polling thread has seen the producer's counters
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+    const bool dflow = p.sync.dep_mode != DEP_PDL;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
     const int pair_local = blockIdx.z;
     const int row0 = blockIdx.x * kTile;
+    const int sync_tile = (pair_local * p.nq + row0) / kTile;      // this CTA's 128-row tile of the launch's row space (nq % 128 == 0 in tile modes)
 
     if (threadIdx.x == 0) {
         mbar_init(qk_full, kSoftmaxThreads);
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         mbar_init(&p_full[1], kSoftmaxThreads);
         mbar_init(&p_empty[0], 1);
         mbar_init(&p_empty[1], 1);
+        mbar_init(dep_ready, 1);
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc(tmem_ptr, 512);
@@ -105,8 +109,11 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         const bool row_ok = qi < p.nq;
         const size_t grow = (size_t)pair_local * p.nq + (row_ok ? qi : 0);
         const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
-        if (t == 0) pdl_launch_dependents();             // the next kernel may start its prologue on idle SMs
-        pdl_wait();                                      // prologue above overlaps the previous kernel
+        if (t == 0) {
+            pdl_launch_dependents();                     // the next kernel may start its prologue on idle SMs
+            if (dflow) { dep_wait_thread(p.sync, sync_tile); mbar_arrive(dep_ready); }
+        }
+        if (dflow) mbar_wait(dep_ready, 0); else pdl_wait();      // prologue above overlaps the previous kernel
         if (t == 0) COTR_TS(2);
 
         // ---- stage Q (row t % 128, two of the four 16-byte K groups per thread) and K (4 keys per thread) --------
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
 
     tcgen05_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) dep_signal_thread(p.sync, sync_tile);
     if (warp == 8) tmem_dealloc(tmem_base, 512);
     if (threadIdx.x == 0) COTR_TS(60);
     if (my_ts && threadIdx.x == 0) my_ts[62] = global_ns();

@@ -88,12 +88,16 @@ struct Cfg {
     static constexpr int kChunksW = kChunksN / kEpiHalves;             // 16-column chunks per epilogue warp
     static constexpr int kRing = kChunksW < 4 ? kChunksW : 4;          // epilogue operand prefetch depth
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
-    static constexpr uint32_t kSmemBytes = kStages * kStage + 2048;     // + alignment slack + barriers
+    // behind the stages: 256 bytes of barriers, then the per-column vectors of the deferred LayerNorm (column sums of
+    // W' or gamma | beta of this tile's BN columns, staged by two idle warps while the main loop runs), then split-K partials
+    static constexpr uint32_t kVecOffset = kStages * kStage + 256;
+    static constexpr uint32_t kVecBytes = 2u * BN * 4u + 2u * BM * 8u;   // + (mean, rstd) of the 128 A rows and of the 128 residual rows
+    static constexpr uint32_t kSmemBytes = kStages * kStage + 2048 + kVecBytes;     // + alignment slack + barriers + vectors
     // split-K (reduce-scatter over the rows): every CTA of the cluster finishes 128 / ksplit rows of the tile and
     // receives the other CTAs' fp32 partial rows behind the barriers (a dedicated region, so peers may push while this
     // CTA's pipeline is still running); rows of BN * 4 bytes, 16-byte pieces XOR-swizzled by row % 8 (thread-per-row
     // accesses would otherwise all land in the same banks)
-    static constexpr uint32_t kPartOffset = kStages * kStage + 256;
+    static constexpr uint32_t kPartOffset = kVecOffset + kVecBytes;
     static constexpr uint32_t kPartPitch = BN * 4u;
     static constexpr int kMaxSplit = BN <= 64 ? 4 : 1;
     static constexpr uint32_t kPartMaxBytes = kMaxSplit > 1 ? 96u * kPartPitch : 0u;   // ksplit 4: 3 x 32 rows; 2: 1 x 64 rows
@@ -126,7 +130,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     uint64_t* empty = bars + 2 * C::kStages;
     uint64_t* accum_full = bars + 3 * C::kStages;
     uint64_t* part_full = bars + 3 * C::kStages + 1;       // split-K leader: all peers' partial tiles have landed
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 2);
+    uint64_t* vec_full = bars + 3 * C::kStages + 2;        // deferred LayerNorm: the per-column vectors are staged
+    uint64_t* dep_ready = bars + 3 * C::kStages + 3;       // dataflow mode: the polling thread has seen the producer's counters
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 4);
+    const bool dflow = p.sync.dep_mode != DEP_PDL;         // counters in global memory instead of griddepcontrol.wait (common.cuh)
+    float* vec_a = reinterpret_cast<float*>(stage_base + C::kVecOffset);      // a_ln: column sums of W'; res_ln: gamma
+    float* vec_b = vec_a + BN;                                                  //                         res_ln: beta
+    float2* st_a = reinterpret_cast<float2*>(vec_b + BN);                       // (mean, rstd) of the A rows of this tile
+    float2* st_r = st_a + BM;                                                   // (mean, rstd) of the residual rows
     // deferred LayerNorm (GemmParams::a_ln_cs / res_ln_part / ln_part_out): only the row-major loader instantiations carry it
     constexpr bool kCanLnA = (MODE == LD_GATHER) && !LN;
     const bool has_aln = kCanLnA && p.a_ln_cs != nullptr;
@@ -146,12 +157,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(&full_a[s], 128);
+            mbar_init(&full_a[s], 129);
             mbar_init(&full_b[s], 1);
             mbar_init(&empty[s], 1);
         }
         mbar_init(accum_full, 1);
         mbar_init(part_full, 1);
+        mbar_init(vec_full, 64);
+        mbar_init(dep_ready, 1);
         mbar_fence_init();
         if (ksplit > 1) mbar_arrive_expect_tx(part_full, (uint32_t)(ksplit - 1) * (uint32_t)(BM / ksplit) * C::kPartPitch);
     }
@@ -178,8 +191,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         // Let the next kernel of the stream / graph start its prologue (barriers, TMEM, weight TMA) on idle SMs now; it
         // still waits (griddepcontrol.wait) for this grid to complete before touching activations.  (Same-box A/B:
         // triggering here beats triggering after the wait by 0.5%, triggering at kernel entry loses 1.4%.)
-        if (threadIdx.x == 0) pdl_launch_dependents();
-        pdl_wait();
+        if (threadIdx.x == 0) {
+            pdl_launch_dependents();
+            if (dflow) { dep_wait_thread(p.sync, blockIdx.x); mbar_arrive(dep_ready); }
+        }
+        if (dflow) mbar_wait(dep_ready, 0); else pdl_wait();
         if (threadIdx.x == 0) COTR_TS(2);
 
 #pragma unroll 1
@@ -268,12 +284,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 const int s = it % C::kStages;
                 const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_b[s], 2u * C::kBPlane);
+                mbar_arrive_expect_tx(&full_a[s], 2u * C::kBPlane);
                 uint8_t* b_dst = stage_base + (size_t)s * C::kStage + 2 * kAPlane;
                 // image: [k chunk][plane][npad rows][128 bytes]; the BN rows of this tile are contiguous per plane
                 const uint8_t* src = wimg + (((size_t)(it0 + it) * 2) * npad + n0) * 128;
-                tma_bulk_g2s(b_dst, src, C::kBPlane, &full_b[s]);
-                tma_bulk_g2s(b_dst + C::kBPlane, src + (size_t)npad * 128, C::kBPlane, &full_b[s]);
+                tma_bulk_g2s(b_dst, src, C::kBPlane, &full_a[s]);
+                tma_bulk_g2s(b_dst + C::kBPlane, src + (size_t)npad * 128, C::kBPlane, &full_a[s]);
                 if (it < 8) COTR_TS(44 + it);
             }
         }
@@ -292,7 +308,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
                 mbar_wait(&full_a[s], ph);
                 if (it < 8) COTR_TS(24 + 2 * it);
-                mbar_wait(&full_b[s], ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(stage_base + (size_t)s * C::kStage);
                 const uint32_t a_h0 = desc_lo_sw128(a_addr);
@@ -323,6 +338,64 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             COTR_TS(41);
         }
         __syncwarp();
+    } else if (kCanLnA && !LN && (has_aln || p.res_ln_part != nullptr)) {
+        // ================= warps 6-7: operands of the deferred LayerNorm ==========================================
+        // (1) the constant per-column vectors of this tile (model constants: their loads are issued before the
+        // dependency wait and land while it lasts);
+        const int u = (warp - 6) * 32 + lane;
+        const float* src_a = has_aln ? p.a_ln_cs : p.res_ln_gamma;
+        float va[(BN + 63) / 64], vb[(BN + 63) / 64];
+#pragma unroll
+        for (int k = 0; k < (BN + 63) / 64; ++k) {
+            const int i = u + 64 * k;
+            const bool ok = i < BN && n0 + i < p.N;
+            va[k] = ok ? __ldg(src_a + n0 + i) : 0.f;
+            vb[k] = (ok && !has_aln) ? __ldg(p.res_ln_beta + n0 + i) : 0.f;
+        }
+        if (dflow) mbar_wait(dep_ready, 0); else pdl_wait();
+        // (2) (mean, rstd) of the 128 rows of this tile from the 16 partial statistics per row their producer's epilogue
+        // left behind ((mean, M2) per 16-column chunk, GemmParams::ln_part_out).  8 lanes read one row's 128-byte line
+        // (coalesced: 4 rows per instruction, all 16 loads of a lane in flight before the first use) and add up
+        //     S1 = sum mean_i,  S2 = sum mean_i^2,  S3 = sum M2_i     (3 butterfly steps)
+        // -> mean = S1 / 16,  M2 = S3 + 16 (S2 - S1^2 / 16)  (the chunk means are of the row's own magnitude, so the
+        // difference is benign).  ld.global.cg, never .nc: the producer may still have been running when this CTA
+        // became resident (see load8_split).
+        auto stage_stats = [&](const float2* part, float2* dst) {
+            const int sub = lane & 7;                      // which 16 bytes (2 partials) of the row's line
+            float4 ld[16];
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int grow = m0 + (warp - 6) * 64 + it * 4 + (lane >> 3);
+                ld[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow < p.M) ld[it] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)grow * 16) + sub);
+            }
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const float4 t4 = ld[it];
+                // chunk means relative to the row's first chunk mean: the sums below then do not cancel
+                const float ref = __shfl_sync(0xffffffffu, t4.x, lane & ~7);
+                const float d0 = t4.x - ref, d1 = t4.z - ref;
+                float s1 = d0 + d1;
+                float s2 = fmaf(d0, d0, d1 * d1);
+                float s3 = t4.y + t4.w;
+#pragma unroll
+                for (int step = 1; step < 8; step <<= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, step);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, step);
+                    s3 += __shfl_xor_sync(0xffffffffu, s3, step);
+                }
+                const float mean = fmaf(s1, 1.f / 16.f, ref);
+                const float m2 = s3 + fmaxf(fmaf(16.f, s2, -s1 * s1), 0.f);          // sum M2_i + 16 sum (mean_i - mean)^2
+                if (sub == 0) dst[(warp - 6) * 64 + it * 4 + (lane >> 3)] = make_float2(mean, rsqrtf(m2 * (1.f / 256.f) + 1e-5f));
+            }
+        };
+        for (int k = 0; k < (BN + 63) / 64; ++k) {
+            const int i = u + 64 * k;
+            if (i < BN) { vec_a[i] = va[k]; vec_b[i] = vb[k]; }
+        }
+        if (has_aln) stage_stats(p.a_ln_part, st_a);
+        if (p.res_ln_part != nullptr) stage_stats(p.res_ln_part, st_r);
+        mbar_arrive(vec_full);
     }
 
     // ================= epilogue: TMEM -> registers -> global ======================================================
@@ -331,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     const int half = warp >> 2;              // column half of the tile it handles
     if (ksplit > 1) cluster_wait();          // every CTA of the cluster has started (long ago by now)
     if (half < C::kEpiHalves) {
-        if (warp >= 4) pdl_wait();           // residual / add operands come from the previous kernels
+        if (warp >= 4) { if (dflow) mbar_wait(dep_ready, 0); else pdl_wait(); }      // residual / add operands come from the previous kernels
         const int cbeg = half * C::kChunksW * 16;
         const int row = m0 + ew * 32 + lane;
         // split-K: lane quarter q is finished by CTA q * ksplit / 4; the other CTAs only contribute partial sums
@@ -343,39 +416,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         const bool has_res = row_ok && p.res.hi != nullptr;
         const size_t res_off = (size_t)(row_ok ? row : 0) * p.ldr;
         const float acc_scale = p.acc_scale;
-        // Deferred LayerNorm: (mean, rstd) of a 256-wide row from the 16 partial statistics its producer's epilogue
-        // left behind (one (mean, M2) pair per 16-column chunk, GemmParams::ln_part_out), merged exactly (Chan et al.):
-        // M2 = sum M2_i + 16 sum (mean_i - mean)^2.  One 128-byte line per row, read with ld.global.cg (never .nc: the
-        // producer is a kernel that may still have been running when this one became resident, see load8_split),
-        // issued here - before the accumulator is ready - so the latency hides behind the main loop.
-        auto row_stats = [&](const float2* part) {
-            float2 pr[16];
-            const float4* src = reinterpret_cast<const float4*>(part + (size_t)row * 16);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 t4 = __ldcg(src + j);
-                pr[2 * j] = make_float2(t4.x, t4.y);
-                pr[2 * j + 1] = make_float2(t4.z, t4.w);
-            }
-            float mean = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) mean += pr[j].x;
-            mean *= (1.f / 16.f);
-            float m2 = 0.f, dev = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                m2 += pr[j].y;
-                const float d = pr[j].x - mean;
-                dev = fmaf(d, d, dev);
-            }
-            const float var = fmaf(16.f, dev, m2) * (1.f / 256.f);
-            return make_float2(mean, 1.f / sqrtf(var + 1e-5f));
-        };
+        // Deferred LayerNorm: (mean, rstd) of this thread's A row / residual row, staged by warps 6-7
         const bool res_ln = kCanLnA && has_res && p.res_ln_part != nullptr;
         float2 res_st = make_float2(0.f, 1.f);
-        if (kCanLnA && res_ln) res_st = row_stats(p.res_ln_part);
-        float2 a_st = make_float2(0.f, 1.f);            // (mean, rstd) of this thread's A row
-        if (kCanLnA && has_aln && row_ok) a_st = row_stats(p.a_ln_part);
+        float res_shift = 0.f;                          // -mean * rstd of the residual row
+        float2 a_st = make_float2(0.f, 1.f);
         const bool emit_part = kCanLnA && row_ok && p.ln_part_out != nullptr;
         const bool tail = p.out_f32 != nullptr && (p.N & 15) != 0;      // only the N = 2 prediction head
         const bool has_bias = p.bias != nullptr && !tail;
@@ -400,10 +445,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             }
         };
         auto apply = [&](const EpiOperands& o, float (&v)[16], int nb) {
+            const int cl = nb - n0;                   // column inside the tile (the staged vectors are tile-local)
             if (kCanLnA && has_aln) {                 // y = rstd * (x W'^T - mean * colsum(W'))
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 cs4 = __ldg(reinterpret_cast<const float4*>(p.a_ln_cs + nb) + j);
+                    const float4 cs4 = *reinterpret_cast<const float4*>(vec_a + cl + 4 * j);
                     v[4 * j] = a_st.y * fmaf(-a_st.x, cs4.x, v[4 * j]);
                     v[4 * j + 1] = a_st.y * fmaf(-a_st.x, cs4.y, v[4 * j + 1]);
                     v[4 * j + 2] = a_st.y * fmaf(-a_st.x, cs4.z, v[4 * j + 2]);
@@ -427,10 +473,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     for (int q = 0; q < 4; ++q) {
                         float2 f = join_f16x2(h[q], l[q]);
                         if (kCanLnA && res_ln) {      // the residual is a deferred LayerNorm of the stored rows
-                            const float2 g2 = __ldg(reinterpret_cast<const float2*>(p.res_ln_gamma + nb + 8 * j + 2 * q));
-                            const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.res_ln_beta + nb + 8 * j + 2 * q));
-                            f.x = fmaf((f.x - res_st.x) * res_st.y, g2.x, b2.x);
-                            f.y = fmaf((f.y - res_st.x) * res_st.y, g2.y, b2.y);
+                            const float2 g2 = *reinterpret_cast<const float2*>(vec_a + cl + 8 * j + 2 * q);
+                            const float2 b2 = *reinterpret_cast<const float2*>(vec_b + cl + 8 * j + 2 * q);
+                            f.x = fmaf(fmaf(f.x, res_st.y, res_shift), g2.x, b2.x);
+                            f.y = fmaf(fmaf(f.y, res_st.y, res_shift), g2.y, b2.y);
                         }
                         v[8 * j + 2 * q] += f.x;
                         v[8 * j + 2 * q + 1] += f.y;
@@ -565,6 +611,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         for (int i = 0; i < C::kRing; ++i) prefetch(nbase + 16 * i, ops[i]);
         mbar_wait(accum_full, 0);
         tcgen05_fence_after();
+        if (kCanLnA && (has_aln || p.res_ln_part != nullptr)) {
+            mbar_wait(vec_full, 0);
+            if (has_aln) a_st = st_a[ew * 32 + lane];
+            if (res_ln) { res_st = st_r[ew * 32 + lane]; res_shift = -res_st.x * res_st.y; }
+        }
         if (threadIdx.x == 0) COTR_TS(20);
         // Narrow tiles read their own accumulators into registers right away: senders push them, owners overlap the
         // TMEM round trips with the wait for the peers' partial rows.
@@ -699,11 +750,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 
     tcgen05_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) dep_signal_thread(p.sync, blockIdx.x);       // every store of this CTA precedes the barrier above
     if (warp == 5) tmem_dealloc(tmem_base, C::kTmemCols);
     if (threadIdx.x == 160) COTR_TS(60);
     if (my_ts && threadIdx.x == 160) my_ts[62] = global_ns();
 #undef COTR_TS
 }
+
+thread_local GemmLaunchInfo* g_launch_info = nullptr;       // where launch_one reports the grid it chose
 
 template <int BN, bool LN, int MODE>
 int launch_one(const GemmParams& p, cudaStream_t s) {
@@ -733,6 +787,7 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     COTR_CHECK(p.ln_part_out == nullptr || (p.N == 256 && !p.remap && p.out_f32 == nullptr), "gemm_tc: row statistics need a plain N = 256 output");
     grid.z = ksplit;
     const size_t smem = C::kSmemBytes + (size_t)(ksplit - 1) * (BM / ksplit) * C::kPartPitch;     // incoming partial rows
+    if (g_launch_info) *g_launch_info = GemmLaunchInfo{(int)grid.x, (int)grid.y, ksplit};
     COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), smem, s, ksplit, p, npad, next_trace_block()));
     return 0;
 }
@@ -825,7 +880,11 @@ float tc_pack_weight(const float* w, int N, int K, void* dst_host) {
     return ldexpf(1.f, -e);
 }
 
-int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
+int launch_gemm_tc(const GemmParams& p, cudaStream_t s, GemmLaunchInfo* info) {
+    struct InfoScope {          // launch_one fills *info through the thread-local pointer
+        explicit InfoScope(GemmLaunchInfo* i) { g_launch_info = i; }
+        ~InfoScope() { g_launch_info = nullptr; }
+    } scope(info);
     COTR_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "gemm_tc: empty problem %d x %d x %d", p.M, p.N, p.K);
     COTR_CHECK(p.Wtc != nullptr, "gemm_tc: weight has no tensor-core image");
     COTR_CHECK(p.out_f32 != nullptr || (p.N & 15) == 0, "gemm_tc: split16 outputs need N %% 16 == 0 (N=%d)", p.N);

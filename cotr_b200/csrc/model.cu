@@ -1,6 +1,7 @@
 // Model state, weight packing, workspace and the forward schedule behind the C ABI (include/cotr_b200.h).
 //
 // Reference lines restated by each stage are cited inline (paths relative to the reference root).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -80,6 +81,8 @@ struct Workspace {
     Split16 stem = kNoSplit, bx = kNoSplit, by = kNoSplit, bt1 = kNoSplit, bt2 = kNoSplit, bds = kNoSplit;
     // encoder
     Split16 src = kNoSplit, xa = kNoSplit, xb = kNoSplit, qk = kNoSplit, vt = kNoSplit, ao = kNoSplit, ffh = kNoSplit;
+    Split16 qk2 = kNoSplit, vt2 = kNoSplit;      // odd encoder layers: with tile-level dependencies layer l+1 projects while layer l still attends
+    int* sync_ctr = nullptr;      // dataflow counter blocks (common.cuh LaunchSync): kSyncBlocks x kSyncBlockInts ints
     float* ln_tmp = nullptr;      // fp32 [tokens][256]: pre-LayerNorm rows of the SIMT cross-check path
     float2 *enc_st_a = nullptr, *enc_st_b = nullptr;     // [tokens][16] partial row statistics of xa / xb (deferred LayerNorms)
     // decoder
@@ -134,6 +137,7 @@ struct cotr_model {
     std::map<long long, int> graph_launches;
     std::set<long long> shapes_seen;
     cotr::Preprocessor* pre = nullptr;         // device-side crop / resize / normalise (cotr_preprocess)
+    cotr::FlowMerger* merger = nullptr;        // device-side tail of the dense first guess (cotr_flow_tile_merge)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_events;      // 2 per record
     std::vector<cotr_launch_record> prof_records;
@@ -281,10 +285,57 @@ std::vector<float> grid_position_table() {
 // ----------------------------------------------------------------------------------------------
 // launch helpers (all kernel launches of the forward go through these, so they can be counted / profiled)
 // ----------------------------------------------------------------------------------------------
+// Dataflow dependencies between the launches of one call (common.cuh LaunchSync): the planner hands every launch the
+// counter block of its predecessor (what to wait for) and a fresh block of its own (where to announce its tiles).
+struct SyncPlan {
+    int* base = nullptr;       // counter blocks of this call (zeroed by the caller)
+    int cap_blocks = 0;
+    int next = 0;
+    bool on = false;
+    const int* prev = nullptr;             // the previous launch's block; null: it announced nothing -> hardware wait
+    int prev_total = 0, prev_tile_target = 0, prev_tiles = 0, prev_rows = -1;
+};
+
 struct Run {
     cotr_model* m;
     cudaStream_t s;
+    SyncPlan* sp = nullptr;
 };
+
+// mode: what this launch would like to wait for (degraded to DEP_ALL when the producer's row tiling does not match);
+// rows: size of this launch's row space; returns the LaunchSync with the dependency part and the signal block filled.
+LaunchSync plan_dep(const Run& r, int mode, int rows, int span = 0) {
+    LaunchSync y;
+    memset(&y, 0, sizeof(y));
+    SyncPlan* sp = r.sp;
+    if (!sp || !sp->on) return y;
+    if (sp->prev) {
+        const bool tile_ok = sp->prev_tiles > 0 && sp->prev_rows == rows;
+        y.dep = sp->prev;
+        if (mode == DEP_TILE && tile_ok) { y.dep_mode = DEP_TILE; y.dep_target = sp->prev_tile_target; }
+        else if (mode == DEP_SPAN && tile_ok && span > 0 && sp->prev_tiles % span == 0) { y.dep_mode = DEP_SPAN; y.dep_span = span; y.dep_target = sp->prev_tile_target; }
+        else { y.dep_mode = DEP_ALL; y.dep_target = sp->prev_total; }
+    }
+    if (sp->next < sp->cap_blocks) {
+        y.sig = sp->base + (size_t)sp->next * kSyncBlockInts;
+        sp->next++;
+    }
+    return y;
+}
+// after the launch: what the NEXT launch may wait for
+void plan_done(const Run& r, const LaunchSync& y, int total, int tile_target, int rows) {
+    SyncPlan* sp = r.sp;
+    if (!sp || !sp->on) return;
+    sp->prev = y.sig;
+    sp->prev_total = total;
+    sp->prev_tile_target = tile_target;
+    sp->prev_tiles = y.sig ? y.sig_tiles : 0;
+    sp->prev_rows = rows;
+}
+inline int sync_tiles_for(int rows) {          // per-tile counters only while they fit the block
+    const int t = (rows + 127) / 128;
+    return t <= kSyncBlockInts - 1 ? t : 0;
+}
 
 enum KernelId { K_GEMM_TC = 0, K_GEMM_SIMT = 1, K_ATTN_TC = 2, K_ATTN_SIMT = 3, K_LAYERNORM = 4, K_MAXPOOL = 5, K_QENC = 6 };
 
@@ -324,8 +375,21 @@ GemmParams gemm_base(int M, int N, int K, CSplit16 A, int lda, const float* W, c
     return p;
 }
 
+// One tcgen05 GEMM launch with its dataflow bookkeeping.  dep_mode: DEP_ALL / DEP_TILE (the A rows of a CTA's tile come
+// from the same 128-row tile of the previous launch, and nothing this launch overwrites is still read by other tiles).
+int launch_tc(const Run& r, GemmParams& p, int dep_mode = DEP_ALL) {
+    p.sync = plan_dep(r, dep_mode, p.M);
+    p.sync.sig_tiles = p.sync.sig ? sync_tiles_for(p.M) : 0;
+    GemmLaunchInfo info{0, 0, 1};
+    LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
+    if (launch_gemm_tc(p, r.s, &info)) return 1;
+    plan_done(r, p.sync, info.row_tiles * info.col_tiles * info.ksplit, info.col_tiles * info.ksplit, p.M);
+    return 0;
+}
+
 // ln_scratch: fp32 [M][256] staging for the SIMT path (the tensor-core GEMM fuses LayerNorm into its epilogue).
-int run_gemm(const Run& r, GemmParams p, float* ln_scratch) {
+int run_gemm(const Run& r, GemmParams p, float* ln_scratch, int dep_mode = DEP_ALL) {
+    if (r.m->gemm_path == 0 && p.ln_gamma == nullptr) return launch_tc(r, p, dep_mode);
     if (r.m->gemm_path == 0) {
         // The fused LayerNorm epilogue needs the whole 256-wide row in one CTA (128 x 256 tile): with few rows that is
         // a handful of CTAs doing a long serial epilogue while the other SMs idle.  Below ~64 row tiles the GEMM runs
@@ -334,6 +398,8 @@ int run_gemm(const Run& r, GemmParams p, float* ln_scratch) {
         const float* g = p.ln_gamma;
         const float* b = p.ln_beta;
         if (defuse) { p.ln_gamma = nullptr; p.ln_beta = nullptr; }
+        // (legacy schedule, not used by the deferred-LayerNorm forward: no dataflow announcements)
+        if (r.sp) r.sp->prev = nullptr;
         {
             LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
             if (launch_gemm_tc(p, r.s)) return 1;
@@ -363,13 +429,13 @@ int run_gemm(const Run& r, GemmParams p, float* ln_scratch) {
 
 int run_linear(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda, Split16 out, int ldc, bool relu,
                CSplit16 residual = CSplit16{nullptr, nullptr}, int ldr = 0, const float* ln_g = nullptr,
-               const float* ln_b = nullptr, float* ln_scratch = nullptr) {
+               const float* ln_b = nullptr, float* ln_scratch = nullptr, int dep_mode = DEP_ALL) {
     GemmParams p = gemm_base(M, L.n, L.k, A, lda, L.w, L.wtc, L.wtc_scale, out, ldc);
     p.bias = L.b;
     p.relu = relu ? 1 : 0;
     p.res = residual; p.ldr = ldr;
     p.ln_gamma = ln_g; p.ln_beta = ln_b;
-    return run_gemm(r, p, ln_scratch);
+    return run_gemm(r, p, ln_scratch, dep_mode);
 }
 
 // Tensor-core path only: linear layer with deferred LayerNorms (GemmParams::a_ln_cs / res_ln_part / ln_part_out).
@@ -378,7 +444,7 @@ int run_linear(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda, Spl
 //   res_part   non-null: the residual operand is a deferred LayerNorm (res_g, res_b) of the stored rows
 int run_linear_dln(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda, Split16 out, int ldc, bool relu,
                    const float2* a_part, float2* part_out, CSplit16 residual = CSplit16{nullptr, nullptr}, int ldr = 0,
-                   const float2* res_part = nullptr, const float* res_g = nullptr, const float* res_b = nullptr) {
+                   const float2* res_part = nullptr, const float* res_g = nullptr, const float* res_b = nullptr, int dep_mode = DEP_TILE) {
     GemmParams p = gemm_base(M, L.n, L.k, A, lda, L.w, L.wtc, L.wtc_scale, out, ldc);
     p.bias = a_part ? L.b_tc : L.b;
     p.relu = relu ? 1 : 0;
@@ -386,8 +452,7 @@ int run_linear_dln(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda,
     if (a_part) { p.a_ln_cs = L.cs; p.a_ln_part = a_part; }
     p.ln_part_out = part_out;
     p.res_ln_part = res_part; p.res_ln_gamma = res_g; p.res_ln_beta = res_b;
-    LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
-    return launch_gemm_tc(p, r.s);
+    return launch_tc(r, p, dep_mode);
 }
 
 int run_conv(const Run& r, const DevConv& c, int n_img, CSplit16 in, const float* in_f32, int H, int W, Split16 out,
@@ -411,11 +476,23 @@ int run_conv(const Run& r, const DevConv& c, int n_img, CSplit16 in, const float
     return run_gemm(r, p, nullptr);
 }
 
-int run_attention(const Run& r, const AttnParams& p) {
+// dep_mode / span: DEP_TILE (decoder: a CTA reads only its own 128 query rows from the previous launch) or DEP_SPAN
+// (encoder: the keys and values of the whole pair, `span` row tiles); both need query tiles aligned with 128-row tiles
+int run_attention(const Run& r, AttnParams p, int dep_mode = DEP_ALL, int span = 0) {
     // recorded as M = query rows, N = 512 keys, K = 32 x 8 heads
-    LaunchScope scope(r, r.m->gemm_path == 0 ? K_ATTN_TC : K_ATTN_SIMT, p.nq * p.npairs, kTokens, kDModel);
-    if (r.m->gemm_path == 0) return launch_attention_tc(p, r.s);
-    return launch_attention_simt(p, r.s);
+    const int rows = p.nq * p.npairs;
+    LaunchScope scope(r, r.m->gemm_path == 0 ? K_ATTN_TC : K_ATTN_SIMT, rows, kTokens, kDModel);
+    if (r.m->gemm_path != 0) return launch_attention_simt(p, r.s);
+    if (p.nq < 32) {                          // launch_attention_tc hands these to the SIMT kernel: hardware wait, no announcements
+        if (r.sp) r.sp->prev = nullptr;
+        return launch_attention_tc(p, r.s);
+    }
+    const bool aligned = (p.nq % 128) == 0;
+    p.sync = plan_dep(r, aligned ? dep_mode : DEP_ALL, rows, span);
+    p.sync.sig_tiles = (p.sync.sig && aligned) ? sync_tiles_for(rows) : 0;
+    if (launch_attention_tc(p, r.s)) return 1;
+    plan_done(r, p.sync, ((p.nq + 127) / 128) * kHeads * p.npairs, kHeads, rows);
+    return 0;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -429,8 +506,8 @@ constexpr size_t kT2Elems = 64 * 64 * 64;          // largest conv2 output per i
 size_t encode_ws_elems(int B) {
     const size_t img = 2 * (size_t)B;
     const size_t tok = (size_t)B * kTokens;
-    return img * (kStemElems + 3 * kBigElems + kT1Elems + kT2Elems) + tok * (kDModel * 4 + 2 * kDModel + kFF) +
-           (size_t)B * kVtLayer + tok * kDModel /* fp32 LN scratch */ + tok * 64 /* row statistics */;
+    return img * (kStemElems + 3 * kBigElems + kT1Elems + kT2Elems) + tok * (kDModel * 4 + 4 * kDModel + kFF) +
+           2 * (size_t)B * kVtLayer + tok * kDModel /* fp32 LN scratch */ + tok * 64 /* row statistics */;
 }
 size_t decode_ws_elems(int rows) {
     return (size_t)rows * (kDModel * 8 + kQpCols + kFF) + (size_t)rows * kDModel /* fp32 LN scratch */ + (size_t)rows * 64 /* row statistics */;
@@ -450,6 +527,19 @@ int ws_alloc_f32(float** p, size_t elems) {
     return 0;
 }
 void ws_free_f32(float** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+// Dataflow counters: kSyncEncodeBlocks for cotr_encode_context, kSyncChunkBlocks per decoder chunk behind them.
+constexpr int kSyncEncodeBlocks = 128;
+constexpr int kSyncChunkBlocks = 48;
+constexpr int kSyncBlocks = 1024;
+
+int ensure_sync_ctr(cotr_model* m) {
+    if (m->ws.sync_ctr) return 0;
+    COTR_CHECK_CUDA(cudaMalloc((void**)&m->ws.sync_ctr, (size_t)kSyncBlocks * kSyncBlockInts * sizeof(int)));
+    return 0;
+}
+// bring-up switch: cotr_debug_set_variant bit 18 turns the dataflow dependencies off (hardware griddepcontrol.wait everywhere)
+inline bool dataflow_enabled(const cotr_model* m) { return m->gemm_path == 0 && !(g_tc_variant & (1 << 18)) && g_use_pdl; }
 
 // Captured graphs embed workspace / staging / context addresses: whenever one of those is reallocated every graph is
 // stale.  The shapes stay "seen", so the next call of each shape re-captures against the new buffers.
@@ -480,7 +570,7 @@ int ensure_encode_ws(cotr_model* m, int B) {
     if (B <= w.cap_pairs) return 0;
     COTR_CHECK_CUDA(cudaDeviceSynchronize());
     drop_graphs(m);
-    Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh};
+    Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh, &w.qk2, &w.vt2};
     for (Split16* b : bufs) ws_free(b);
     ws_free_f32(&w.ln_tmp);
     ws_free_f32(reinterpret_cast<float**>(&w.enc_st_a));
@@ -490,6 +580,7 @@ int ensure_encode_ws(cotr_model* m, int B) {
         ws_alloc(&w.bds, img * kBigElems) || ws_alloc(&w.bt1, img * kT1Elems) || ws_alloc(&w.bt2, img * kT2Elems) ||
         ws_alloc(&w.src, tok * kDModel) || ws_alloc(&w.xa, tok * kDModel) || ws_alloc(&w.xb, tok * kDModel) ||
         ws_alloc(&w.qk, tok * 2 * kDModel) || ws_alloc(&w.vt, (size_t)B * kVtLayer) || ws_alloc(&w.ao, tok * kDModel) ||
+        ws_alloc(&w.qk2, tok * 2 * kDModel) || ws_alloc(&w.vt2, (size_t)B * kVtLayer) ||
         ws_alloc(&w.ffh, tok * kFF) || ws_alloc_f32(&w.ln_tmp, tok * kDModel) ||
         ws_alloc_f32(reinterpret_cast<float**>(&w.enc_st_a), tok * 32) || ws_alloc_f32(reinterpret_cast<float**>(&w.enc_st_b), tok * 32))
         return 1;
@@ -526,9 +617,14 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
     COTR_CHECK(ctx && ctx->model == m, "cotr_encode_context: context does not belong to this model");
     COTR_CHECK(B <= ctx->max_pairs, "cotr_encode_context: B = %d exceeds the context capacity %d", B, ctx->max_pairs);
     COTR_CHECK_CUDA(cudaSetDevice(m->device));
-    if (ensure_encode_ws(m, B)) return 1;
+    if (ensure_encode_ws(m, B) || ensure_sync_ctr(m)) return 1;
     Workspace& w = m->ws;
-    Run r{m, s};
+    SyncPlan plan;
+    plan.on = dataflow_enabled(m);
+    plan.base = w.sync_ctr;
+    plan.cap_blocks = kSyncEncodeBlocks;
+    if (plan.on) COTR_CHECK_CUDA(cudaMemsetAsync(w.sync_ctr, 0, (size_t)kSyncEncodeBlocks * kSyncBlockInts * sizeof(int), s));
+    Run r{m, s, &plan};
     const int n_img = 2 * B;
     const CSplit16 none{nullptr, nullptr};
 
@@ -537,7 +633,11 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
     if (run_conv(r, m->stem, n_img, none, img, 256, 256, w.stem, true, none)) return 1;
     {
         LaunchScope scope(r, K_MAXPOOL, n_img * 64 * 64, 64, 0);
-        if (launch_maxpool_3x3s2_nhwc(cs(w.stem), w.bx, n_img, 128, 128, 64, s)) return 1;
+        LaunchSync y = plan_dep(r, DEP_ALL, n_img * 64 * 64);
+        if (launch_maxpool_3x3s2_nhwc(cs(w.stem), w.bx, n_img, 128, 128, 64, s, y)) return 1;
+        const size_t total = (size_t)n_img * 64 * 64 * 8;
+        const size_t blocks = (total + 255) / 256;
+        plan_done(r, y, (int)(blocks < 148 * 16 ? blocks : 148 * 16), 0, n_img * 64 * 64);
     }
 
     Split16 x = w.bx;
@@ -581,23 +681,25 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
         for (int l = 0; l < (n_enc_dbg ? n_enc_dbg : kEncLayers); ++l) {
             const EncLayer& e = m->enc[l];
             const bool ln_in = l > 0;          // the layer input is LN2_{l-1}(xb), deferred
+            // q|k and v^T alternate between two buffers: with tile-level dependencies the next layer's projection of a
+            // row tile may run while other tiles of this layer still attend to the old keys / values
+            const Split16 qk_l = (l & 1) ? w.qk2 : w.qk, vt_l = (l & 1) ? w.vt2 : w.vt;
             {
-                GemmParams p = gemm_base(T, 3 * kDModel, kDModel, cs(xin), kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, w.qk, 2 * kDModel);
+                GemmParams p = gemm_base(T, 3 * kDModel, kDModel, cs(xin), kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, qk_l, 2 * kDModel);
                 p.addmat = e.add_qkv_tc; p.add_period = kTokens; p.ld_add = 3 * kDModel;
                 p.remap = 1;
                 p.blk_map[0] = 0; p.blk_map[1] = kDModel; p.blk_map[2] = -1;
-                p.vt = w.vt; p.n_vt = 1;
+                p.vt = vt_l; p.n_vt = 1;
                 if (ln_in) { p.a_ln_cs = e.qkv.cs; p.a_ln_part = w.enc_st_b; }
-                LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
-                if (launch_gemm_tc(p, r.s)) return 1;
+                if (launch_tc(r, p, DEP_TILE)) return 1;
             }
             AttnParams a;
-            a.q = cs(w.qk); a.ldq = 2 * kDModel;
-            a.k = offset(cs(w.qk), kDModel); a.ldk = 2 * kDModel;
-            a.vt = cs(w.vt); a.vt_pair_stride = kVtLayer;
+            a.q = cs(qk_l); a.ldq = 2 * kDModel;
+            a.k = offset(cs(qk_l), kDModel); a.ldk = 2 * kDModel;
+            a.vt = cs(vt_l); a.vt_pair_stride = kVtLayer;
             a.out = w.ao; a.ldo = kDModel;
             a.nq = kTokens; a.npairs = B; a.pair0 = 0;
-            if (run_attention(r, a)) return 1;
+            if (run_attention(r, a, DEP_SPAN, kTokens / 128)) return 1;
             // xa = x + out_proj(attn)                                   (transformer.py:149-154, norm1 deferred)
             if (run_linear_dln(r, e.o, T, cs(w.ao), kDModel, w.xa, kDModel, false, nullptr, w.enc_st_a, cs(xin), kDModel,
                                ln_in ? w.enc_st_b : nullptr, ln_in ? m->enc[l - 1].ln2_g : nullptr, ln_in ? m->enc[l - 1].ln2_b : nullptr)) return 1;
@@ -621,8 +723,7 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
             }
             p.vt = ctx->vt; p.n_vt = kDecLayers;
             p.a_ln_cs = m->kv_all.cs; p.a_ln_part = w.enc_st_b;
-            LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
-            if (launch_gemm_tc(p, r.s)) return 1;
+            if (launch_tc(r, p, DEP_TILE)) return 1;
         }
         ctx->pairs = B;
         m->last_pairs = B;
@@ -676,19 +777,28 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
 }
 
 int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, float* pred, int pair0, int npairs,
-                 int nq, cudaStream_t s) {
+                 int nq, cudaStream_t s, int chunk_index) {
     Workspace& w = m->ws;
-    Run r{m, s};
+    // dataflow counters of this chunk (zeroed by decode_impl); the chunk's first launch has no announced producer and
+    // falls back to the hardware wait, which also orders it behind the previous chunk / the encoder
+    SyncPlan plan;
+    plan.on = dataflow_enabled(m) && kSyncEncodeBlocks + (chunk_index + 1) * kSyncChunkBlocks <= kSyncBlocks;
+    plan.base = w.sync_ctr + (size_t)(kSyncEncodeBlocks + chunk_index * kSyncChunkBlocks) * kSyncBlockInts;
+    plan.cap_blocks = kSyncChunkBlocks;
+    Run r{m, s, &plan};
     const int R = npairs * nq;
     const CSplit16 none{nullptr, nullptr};
     // cotr_model.py:34-35 query_proj (lin_sine, depth 64)
     {
         LaunchScope scope(r, K_QENC, R, kDModel, 0);
-        if (launch_query_encode(queries, w.qpos, R, s)) return 1;
+        LaunchSync y = plan_dep(r, DEP_ALL, R);
+        y.sig_tiles = (y.sig && (R % 128) == 0) ? sync_tiles_for(R) : 0;      // one block per row: whole tiles only
+        if (launch_query_encode(queries, w.qpos, R, s, y)) return 1;
+        plan_done(r, y, R, 128, R);
     }
     // q-side of transformer.py:192: ((t + qpos) Wq^T + bq) s  =  t (s Wq)^T + [qpos (s Wq)^T + s bq]; the bracket for
     // all 6 layers is one GEMM.
-    if (run_linear(r, m->qpos_all, R, cs(w.qpos), kDModel, w.qp, kQpCols, false)) return 1;
+    if (run_linear(r, m->qpos_all, R, cs(w.qpos), kDModel, w.qp, kQpCols, false, none, 0, nullptr, nullptr, nullptr, DEP_TILE)) return 1;
 
     if (m->gemm_path == 0) {
         // Tensor-core path with deferred LayerNorms (see encode_impl): w.t = t + attention (norm2 deferred),
@@ -709,7 +819,7 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
             a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
             a.out = w.dao; a.ldo = kDModel;
             a.nq = nq; a.npairs = npairs; a.pair0 = pair0;
-            if (run_attention(r, a)) return 1;
+            if (run_attention(r, a, DEP_TILE)) return 1;
             // transformer.py:196-197: t = t + out_proj(attn)   (norm2 deferred; t = norm3_{l-1}(t2), deferred, or 0)
             if (run_linear_dln(r, d.o, R, cs(w.dao), kDModel, w.t, kDModel, false, nullptr, w.dec_st_a, ln_in ? cs(w.t2) : none, kDModel,
                                ln_in ? w.dec_st_b : nullptr, ln_in ? m->dec[l - 1].ln3_g : nullptr, ln_in ? m->dec[l - 1].ln3_b : nullptr)) return 1;
@@ -722,7 +832,10 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
         {
             const DecLayer& d = m->dec[kDecLayers - 1];
             LaunchScope scope(r, K_LAYERNORM, R, kDModel, 0);
-            if (launch_layernorm_twice(cs(w.t2), d.ln3_g, d.ln3_b, m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
+            LaunchSync y = plan_dep(r, DEP_TILE, R);
+            y.sig_tiles = (y.sig && (R % 128) == 0) ? sync_tiles_for(R) : 0;      // 8 rows per block: whole tiles only
+            if (launch_layernorm_twice(cs(w.t2), d.ln3_g, d.ln3_b, m->dec_norm_g, m->dec_norm_b, w.hs, R, s, y)) return 1;
+            plan_done(r, y, (R + 7) / 8, 16, R);
         }
     } else {
         for (int l = 0; l < kDecLayers; ++l) {
@@ -752,13 +865,13 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
             if (launch_layernorm(cs(w.t), m->dec_norm_g, m->dec_norm_b, w.hs, R, s)) return 1;
         }
     }
-    if (run_linear(r, m->head[0], R, cs(w.hs), kDModel, w.hd1, kDModel, true)) return 1;
-    if (run_linear(r, m->head[1], R, cs(w.hd1), kDModel, w.hd2, kDModel, true)) return 1;
+    if (run_linear(r, m->head[0], R, cs(w.hs), kDModel, w.hd1, kDModel, true, none, 0, nullptr, nullptr, nullptr, DEP_TILE)) return 1;
+    if (run_linear(r, m->head[1], R, cs(w.hd1), kDModel, w.hd2, kDModel, true, none, 0, nullptr, nullptr, nullptr, DEP_TILE)) return 1;
     {
         GemmParams p = gemm_base(R, 2, kDModel, cs(w.hd2), kDModel, m->head[2].w, m->head[2].wtc, m->head[2].wtc_scale, kNoSplit, 2);
         p.bias = m->head[2].b;
         p.out_f32 = pred;
-        if (run_gemm(r, p, nullptr)) return 1;
+        if (run_gemm(r, p, nullptr, DEP_TILE)) return 1;
     }
     return 0;
 }
@@ -771,19 +884,32 @@ int decode_impl(cotr_model* m, const cotr_context* ctx, const float* queries, in
     COTR_CHECK_CUDA(cudaSetDevice(m->device));
     const long long total = (long long)B * Q;
     const int cap = (int)(total < kDecodeChunkRows ? total : kDecodeChunkRows);
-    if (ensure_decode_ws(m, cap)) return 1;
+    if (ensure_decode_ws(m, cap) || ensure_sync_ctr(m)) return 1;
+    int n_chunks = 0;
+    if (Q <= kDecodeChunkRows) {
+        const int pairs_per = kDecodeChunkRows / Q;
+        n_chunks = (B + pairs_per - 1) / pairs_per;
+    } else {
+        n_chunks = B * ((Q + kDecodeChunkRows - 1) / kDecodeChunkRows);
+    }
+    if (dataflow_enabled(m)) {
+        const int blocks = std::min(kSyncBlocks - kSyncEncodeBlocks, n_chunks * kSyncChunkBlocks);
+        COTR_CHECK_CUDA(cudaMemsetAsync(m->ws.sync_ctr + (size_t)kSyncEncodeBlocks * kSyncBlockInts, 0,
+                                        (size_t)blocks * kSyncBlockInts * sizeof(int), s));
+    }
+    int chunk = 0;
     if (Q <= kDecodeChunkRows) {
         const int pairs_per = kDecodeChunkRows / Q;
         for (int b0 = 0; b0 < B; b0 += pairs_per) {
             const int nb = (B - b0 < pairs_per) ? B - b0 : pairs_per;
-            if (decode_chunk(m, ctx, queries + (size_t)b0 * Q * 2, pred + (size_t)b0 * Q * 2, b0, nb, Q, s)) return 1;
+            if (decode_chunk(m, ctx, queries + (size_t)b0 * Q * 2, pred + (size_t)b0 * Q * 2, b0, nb, Q, s, chunk++)) return 1;
         }
     } else {
         for (int b = 0; b < B; ++b)
             for (int q0 = 0; q0 < Q; q0 += kDecodeChunkRows) {
                 const int nq = (Q - q0 < kDecodeChunkRows) ? Q - q0 : kDecodeChunkRows;
                 const size_t off = ((size_t)b * Q + q0) * 2;
-                if (decode_chunk(m, ctx, queries + off, pred + off, b, 1, nq, s)) return 1;
+                if (decode_chunk(m, ctx, queries + off, pred + off, b, 1, nq, s, chunk++)) return 1;
             }
     }
     m->last_rows = (total <= kDecodeChunkRows) ? (int)total : 0;
@@ -1008,8 +1134,9 @@ void cotr_destroy(cotr_model* m) {
     for (void* p : m->allocs) cudaFree(p);
     Workspace& w = m->ws;
     Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh,
-                       &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2, &w.t2};
+                       &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2, &w.t2, &w.qk2, &w.vt2};
     for (Split16* b : bufs) ws_free(b);
+    if (w.sync_ctr) cudaFree(w.sync_ctr);
     float** fbufs[] = {&w.ln_tmp, &w.dln_tmp, &w.img_stage, &w.q_stage, &w.pred_stage,
                        reinterpret_cast<float**>(&w.enc_st_a), reinterpret_cast<float**>(&w.enc_st_b),
                        reinterpret_cast<float**>(&w.dec_st_a), reinterpret_cast<float**>(&w.dec_st_b)};
@@ -1017,6 +1144,7 @@ void cotr_destroy(cotr_model* m) {
     if (m->host_stream) cudaStreamDestroy(m->host_stream);
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
     preprocessor_destroy(m->pre);
+    flow_merger_destroy(m->merger);
     for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
     if (m->order_event) cudaEventDestroy(m->order_event);
     delete m;
@@ -1190,6 +1318,22 @@ int cotr_dense_postprocess(cotr_model* m, const float* pred_dev, int n, float* o
     COTR_CHECK(m != nullptr, "cotr_dense_postprocess: null model");
     COTR_CHECK_CUDA(cudaSetDevice(m->device));
     return dense_post_launch(pred_dev, out_dev, n, (cudaStream_t)cuda_stream);
+}
+
+int cotr_flow_tile_merge(cotr_model* m, const float* tile_dev, int pitch_floats, const double* affine_host, int px, int py, int pw, int ph,
+                         int ow, int oh, float* flow_dev, float* conf_dev, int first, void* cuda_stream) {
+    COTR_CHECK(m != nullptr, "cotr_flow_tile_merge: null model");
+    COTR_CHECK_CUDA(cudaSetDevice(m->device));
+    if (!m->merger) m->merger = flow_merger_create();
+    CallOrder order(m, (cudaStream_t)cuda_stream);
+    return flow_tile_merge_launch(m->merger, tile_dev, pitch_floats, affine_host, px, py, pw, ph, ow, oh, flow_dev, conf_dev, first,
+                                  (cudaStream_t)cuda_stream);
+}
+
+int cotr_group_tasks(int device, const double* pts_dev, const double* box_dev, int n, int batch_size, int max_load, int32_t* squad_dev,
+                     int32_t* rank_dev, int32_t* n_squads_dev, void* cuda_stream) {
+    COTR_CHECK_CUDA(cudaSetDevice(device));
+    return group_tasks_launch(pts_dev, box_dev, n, batch_size, max_load, squad_dev, rank_dev, n_squads_dev, (cudaStream_t)cuda_stream);
 }
 
 int cotr_rasterize_triangles(int device, const float* tris_dev, int n_tri, int H, int W, float* out_dev, void* cuda_stream) {

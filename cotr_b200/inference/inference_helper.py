@@ -21,6 +21,7 @@ THRESHOLD_SPARSE = 0.02
 THRESHOLD_PIXELS_RELATIVE = 0.02
 BASE_ZOOM = 1.0
 DEVICE_DENSE_POST = True   # native model: finish the dense pass on the device (cotr_dense_postprocess); False = host path
+DEVICE_FLOW_MERGE = True   # native model: patch affine + float_image_resize + tile merge on the device (cotr_flow_tile_merge)
 THRESHOLD_AREA = 0.02
 LARGE_GPU = True
 
@@ -182,11 +183,49 @@ def _resample(img_src, corr):
     return utils.torch_img_to_np_img(torch.nn.functional.grid_sample(src, torch.from_numpy(corr)[None].float())[0])
 
 
+def _affine_terms(to):
+    """cv2 2x3 affine `to` as the reference applies it (`c[..., :2] @ to[:2, :2] + to[:, 2]`, :157-158) ->
+    [a0..a5] with x' = a0 x + a1 y + a2, y' = a3 x + a4 y + a5."""
+    return [to[0, 0], to[1, 0], to[0, 2], to[0, 1], to[1, 1], to[1, 2]]
+
+
+def _cotr_flow_device(model, patches_a, patches_b):
+    """cotr_patch_flow_exhaustive + merge_flow_patches with every per-tile array left on the device: the dense pass'
+    (256,512,3) answer is split into its halves by pointer, mapped / resized / merged by cotr_flow_tile_merge."""
+    device = _model_device(model)
+    unit = np.array([[-1, -1], [1, -1], [1, 1]], dtype=np.float32)
+    canv = {}
+    for key, p in (("a", patches_a[0]), ("b", patches_b[0])):
+        canv[key] = (torch.empty((p.oh, p.ow, 2), dtype=torch.float32, device=device), torch.empty((p.oh, p.ow), dtype=torch.float32, device=device))
+    first = True
+    queries = torch.from_numpy(_dense_grid().reshape(-1, 2))[None].float().to(device)
+    for p_i in patches_a:
+        for p_j in patches_b:
+            img = _to_network_canvas(p_i.patch, p_j.patch)[None].to(device)
+            pred = model.forward(img, queries)['pred_corrs'].detach()
+            corr = model.dense_postprocess(pred)[0]                           # (256,512,3) on the device
+            to_j = cv2.getAffineTransform(unit, _patch_corners_ndc(p_j))
+            to_i = cv2.getAffineTransform(unit, _patch_corners_ndc(p_i))
+            model.flow_tile_merge(corr[:, :MAX_SIZE, :], _affine_terms(to_j), p_i, canv["a"][0], canv["a"][1], first)
+            model.flow_tile_merge(corr[:, MAX_SIZE:, :], _affine_terms(to_i), p_j, canv["b"][0], canv["b"][1], first)
+            first = False
+    out = []
+    for key in ("a", "b"):
+        flow, conf = canv[key]
+        out.append((flow.cpu().numpy().astype(np.float64), conf.cpu().numpy().astype(np.float64)))   # the reference's arrays are float64
+    return out
+
+
 def cotr_flow(model, img_a, img_b):
     """Dense correspondence maps in [-1,1] + cycle confidence + warped images, both directions (:168-182)."""
-    corrs_a, corrs_b = cotr_patch_flow_exhaustive(model, to_square_patches(img_a), to_square_patches(img_b))
-    corr_a, con_a, _ = merge_flow_patches(corrs_a)
-    corr_b, con_b, _ = merge_flow_patches(corrs_b)
+    patches_a, patches_b = to_square_patches(img_a), to_square_patches(img_b)
+    if (LARGE_GPU and DEVICE_DENSE_POST and DEVICE_FLOW_MERGE and hasattr(model, 'flow_tile_merge') and hasattr(model, 'dense_postprocess')
+            and _model_device(model).type == 'cuda'):
+        (corr_a, con_a), (corr_b, con_b) = _cotr_flow_device(model, patches_a, patches_b)
+    else:
+        corrs_a, corrs_b = cotr_patch_flow_exhaustive(model, patches_a, patches_b)
+        corr_a, con_a, _ = merge_flow_patches(corrs_a)
+        corr_b, con_b, _ = merge_flow_patches(corrs_b)
     return corr_a, con_a, _resample(img_b, corr_a), corr_b, con_b, _resample(img_a, corr_b)
 
 

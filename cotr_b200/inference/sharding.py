@@ -68,6 +68,43 @@ def forward_sharded(model, img, queries, group=None):
     return gather_predictions(local, img.shape[0], group)
 
 
+class AsyncGather:
+    """The result gather of a stream of independent steps, kept off the compute stream's critical path.
+
+    `submit(pred)` enqueues the all-gather of this rank's (b,Q,2) block on a side stream that waits (CUDA event) for the
+    kernels that produce `pred`; the compute stream continues with the next step at once.  Blocks are gathered into
+    one of two alternating buffers (the step after next reuses the first), `wait()` joins the side stream into the
+    current stream and returns the most recent gathered tensor.  NCCL calls are issued in the same order on every
+    rank, which is all NCCL needs; the 8 KB exchange is pure latency, so overlapping it with the next forward hides it."""
+
+    def __init__(self, block_shape, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if _active(group) else 1
+        self.side = torch.cuda.Stream(device=device) if self.world > 1 else None
+        self.bufs = [torch.empty((self.world * block_shape[0],) + tuple(block_shape[1:]), dtype=torch.float32, device=device) for _ in range(2)]
+        self.turn = 0
+        self.last = None
+
+    def submit(self, pred):
+        if self.world == 1:
+            self.last = pred
+            return
+        out = self.bufs[self.turn]
+        self.turn ^= 1
+        ready = torch.cuda.Event()
+        ready.record()                                   # after the kernels of this step on the compute stream
+        pred.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            dist.all_gather_into_tensor(out, pred, group=self.group)
+        self.last = out
+
+    def wait(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        return self.last
+
+
 class LazyCanvases:
     """What `ShardedCOTR.preprocess_canvases` returns: the recipe of n network canvases (two uint8 device images and
     n crop rectangles), materialised per rank for its own block only when the forward is issued."""

@@ -283,10 +283,14 @@ class FasterSparseEngine(SparseEngine):
     left behind at an earlier level never reach 'finished' (SURVEY.md section 3.3).
     """
 
-    def __init__(self, model, batch_size, mode='stretching', max_load=256, device_preprocess=True, rescue_stranded=False):
+    def __init__(self, model, batch_size, mode='stretching', max_load=256, device_preprocess=True, rescue_stranded=False,
+                 device_grouping=True):
         super().__init__(model, batch_size, mode=mode, device_preprocess=device_preprocess)
         self.max_load = max_load
         self.rescue_stranded = rescue_stranded
+        # squads are formed on the device (cotr_group_tasks) whenever the pixels are made there too; the result is
+        # identical to the host walk of form_squad (same order, same strict float64 comparisons)
+        self.device_grouping = device_grouping
         self._squad_pixels_on_device = False
 
     def infer_batch_grouped(self, img_batch, query_batch):
@@ -332,6 +336,60 @@ class FasterSparseEngine(SparseEngine):
         bookkeeping[loads] = False
         return members, img, torch.stack(queries, axis=1), bookkeeping
 
+    @staticmethod
+    def _pilot_boxes(candidates):
+        """(n,8) [f_l, f_r, f_u, f_d, t_l, t_r, t_u, t_d]: the central-half boxes (SAFE_AREA of form_squad) of the crops
+        every candidate would use as a pilot - `get_patch_centered_at` (inference_helper.py:78-102) vectorised over the
+        tasks with the same float64 expressions and the same int() truncations."""
+        first = candidates[0]
+        out = np.empty((len(candidates), 8), dtype=np.float64)
+        sides = ((0, np.array([c.loc_from for c in candidates], dtype=np.float64), np.array([c.s_from * c.cur_zoom for c in candidates]), first.image_from.shape),
+                 (4, np.array([c.cur_loc_to for c in candidates], dtype=np.float64), np.array([c.s_to * c.cur_zoom for c in candidates]), first.image_to.shape))
+        for col, pos, scale, shape in sides:
+            h, w = shape[0], shape[1]
+            size = min(h, w) * np.clip(scale, 0.0, 1.0)
+            size = ((size // 2) * 2).astype(np.int64)
+            top = np.trunc(pos[:, 1] - size // 2).astype(np.int64)
+            left = np.trunc(pos[:, 0] - size // 2).astype(np.int64)
+            top = np.maximum(top, 0)
+            left = np.maximum(left, 0)
+            top = np.where(top + size > h, h - size, top)
+            left = np.where(left + size > w, w - size, left)
+            cx, cy = left + size / 2, top + size / 2
+            out[:, col + 0] = cx - size / 2 * 0.5
+            out[:, col + 1] = cx + size / 2 * 0.5
+            out[:, col + 2] = cy - size / 2 * 0.5
+            out[:, col + 3] = cy + size / 2 * 0.5
+        return out
+
+    def _form_squads_on_device(self, zoom, tasks, tasks_map, task_ids):
+        """form_squad for the whole batch in one device call (cotr_group_tasks); the per-task bookkeeping (`submitted`,
+        `cur_job`, the queries in the pilot's frame) is then replayed on the host in the reference's order."""
+        from .. import capi
+        candidates = [tasks[ti] for ti in task_ids]
+        boxes = self._pilot_boxes(candidates)
+        device = next(self.model.parameters()).device
+        squad, rank, n_squads = capi.group_tasks(tasks_map, boxes, self.batch_size, self.max_load, device)
+        task_ref, queries = [], []
+        order = np.lexsort((rank, squad))
+        order = order[squad[order] >= 0]
+        bounds = np.searchsorted(squad[order], np.arange(n_squads + 1))
+        for s in range(n_squads):
+            idx = order[bounds[s]:bounds[s + 1]]
+            pilot = candidates[idx[0]]
+            assert pilot.status == 'unfinished' and pilot.submitted == False and pilot.cur_zoom == zoom
+            _, query = pilot.get_task_fast()
+            members, qs = [pilot], [query]
+            for i in idx[1:]:
+                t = candidates[i]
+                assert t.status == 'unfinished' and t.submitted == False and t.cur_zoom == zoom
+                _, query = t.get_task_pilot(pilot)
+                members.append(t)
+                qs.append(query)
+            task_ref.append(members)
+            queries.append(torch.stack(qs, axis=1))
+        return task_ref, queries
+
     def form_grouped_batch(self, zoom, tasks):
         """Up to batch_size squads; queries zero-padded to the longest squad (:339-369)."""
         tasks_map, task_ids = self.get_tasks_map(zoom, tasks)
@@ -340,6 +398,13 @@ class FasterSparseEngine(SparseEngine):
         shuffle = np.random.permutation(tasks_map.shape[0])
         tasks_map = np.take(tasks_map, shuffle, axis=0)
         task_ids = np.take(task_ids, shuffle, axis=0)
+        if self._squad_pixels_on_device and self.device_grouping:
+            task_ref, queries = self._form_squads_on_device(zoom, tasks, tasks_map, task_ids)
+            if not task_ref:
+                return [], [], []
+            longest = max(q.shape[1] for q in queries)
+            queries = [torch.cat([q, torch.zeros([1, longest - q.shape[1], 2])], axis=1) for q in queries]
+            return task_ref, self._device_canvases([squad[0] for squad in task_ref]), torch.cat(queries)
         bookkeeping = np.ones_like(task_ids).astype(bool)
         task_ref, imgs, queries = [], [], []
         for i, ti in enumerate(task_ids):

@@ -249,6 +249,12 @@ class COTR(nn.Module):
         return self.native().dense_postprocess(pred)
 
     @torch.no_grad()
+    def flow_tile_merge(self, tile, affine, patch, flow, conf, first):
+        """Device-side `c @ A + t` -> `float_image_resize` -> `merge_flow_patches` step for one 256x256x3 tile answer
+        (inference_helper.py:155-160, :61-75): see cotr_flow_tile_merge in include/cotr_b200.h."""
+        self.native().flow_tile_merge(tile, affine, patch, flow, conf, first)
+
+    @torch.no_grad()
     def encode_context(self, samples, reuse=False):
         x = self._canvas(samples)
         nat = self.native()

@@ -98,6 +98,26 @@ int cotr_preprocess(cotr_model* m, const uint8_t* img_from_dev, int h_from, int 
  * `corr` array before it is split into its two halves (grid_sample: bilinear, zero padding, align_corners = False). */
 int cotr_dense_postprocess(cotr_model* m, const float* pred_dev, int n, float* out_dev, void* cuda_stream);
 
+/* Device-side tail of the dense first guess for ONE (tile of a, tile of b) answer (inference_helper.py:155-160, :61-75,
+ * COTR/utils/utils.py:69-83): tile_dev is a 256 x 256 x 3 fp32 block [x, y, confidence] (row pitch `pitch_floats`, e.g.
+ * one half of cotr_dense_postprocess' output).  (x, y) are mapped by the 2x3 affine `affine_host` (row-major doubles:
+ * x' = a0 x + a1 y + a2, y' = a3 x + a4 y + a5, what cv2.getAffineTransform gives the reference), the three channels are
+ * resized to ph x pw with Pillow's mode-'F' bilinear filter (bit-exact restatement) and merged into the oh x ow canvases
+ * flow_dev (oh, ow, 2) / conf_dev (oh, ow) at (px, py): a pixel takes the tile's value when the tile's confidence is <=
+ * the stored one (ties go to the later tile).  first != 0 initialises the canvases (flow 0, confidence 100) beforehand. */
+int cotr_flow_tile_merge(cotr_model* m, const float* tile_dev, int pitch_floats, const double* affine_host, int px, int py, int pw, int ph,
+                         int ow, int oh, float* flow_dev, float* conf_dev, int first, void* cuda_stream);
+
+/* Squad formation of the grouped scheduler (FasterSparseEngine.form_grouped_batch / form_squad,
+ * COTR/inference/sparse_engine.py:295-369) on the device.  pts_dev: n x 4 fp64 [x_from, y_from, x_to, y_to] of the open
+ * tasks of one zoom level in the engine's (already shuffled) order; box_dev: n x 8 fp64, the central-half boxes
+ * [f_l, f_r, f_u, f_d, t_l, t_r, t_u, t_d] of the two crops task i would impose as a pilot.  In list order every still
+ * free task becomes the pilot of a new squad and takes along the first max_load free tasks strictly inside both of its
+ * boxes, until batch_size squads exist.  squad_dev[i] = squad of task i or -1, rank_dev[i] = position inside the squad
+ * (0 = pilot, members in list order), *n_squads_dev = squads formed.  All arrays DEVICE memory. */
+int cotr_group_tasks(int device, const double* pts_dev, const double* box_dev, int n, int batch_size, int max_load, int32_t* squad_dev,
+                     int32_t* rank_dev, int32_t* n_squads_dev, void* cuda_stream);
+
 /* The rendering half of triangulate_corr (COTR/inference/inference_helper.py:293-308; the reference rasterises the
  * Delaunay triangles of the source points with OpenGL through vispy, vertex colour = target coordinates).
  * tris_dev: n_tri x 3 vertices x 4 fp32 [x, y, u, v] (DEVICE; x, y in pixels of the H x W source image, u, v the values

@@ -202,6 +202,79 @@ def test_triangulate_corr_cuda_rasteriser_matches_oracle(built_lib):
         got_inside = (got != 0).any(axis=2)
         assert (got_inside != inside).mean() < 2e-4                      # hull-edge pixel centres only
         both = got_inside & inside
-        assert both.mean() > 0.2
-        assert np.abs(got[both] - ref[both]).max() < 2e-3                # pixels of the target image (coords up to ~1e3)
+        assert both.sum() > 30 and both.sum() > 0.9 * inside.sum()
+        # pixels of the target image (coordinates up to ~1e3); sliver triangles amplify the fp32 vertex rounding
+        assert np.abs(got[both] - ref[both]).max() < 2e-2 and np.abs(got[both] - ref[both]).mean() < 1e-4
         assert (got[~got_inside] == 0).all()
+
+
+def test_device_flow_merge_equals_host_path(models):
+    """cotr_flow_tile_merge (patch affine + Pillow-exact mode-'F' resize + min-confidence merge on the device) against
+    the reference's host sequence (numpy affine, PIL float resize per channel, merge_flow_patches) on the same dense
+    answers: non-square images, so each side has two overlapping tiles (4 dense passes) and the merge really chooses."""
+    from cotr_b200.inference import inference_helper as ih
+    native, _ = models
+    img_a = synthetic_image(47, 300, 420)
+    img_b = synthetic_image(48, 380, 290)
+    out = {}
+    for flag in (True, False):
+        ih.DEVICE_FLOW_MERGE = flag
+        try:
+            out[flag] = ih.cotr_flow(native, img_a, img_b)
+        finally:
+            ih.DEVICE_FLOW_MERGE = True
+    for k, name in ((0, "corr_a"), (1, "con_a"), (3, "corr_b"), (4, "con_b")):
+        dev, host = out[True][k], out[False][k]
+        assert dev.shape == host.shape and dev.dtype == host.dtype == np.float64
+        # both sides start from the same fp32 dense answers (same kernels, same inputs) and the resampler is restated
+        # exactly (double accumulation, fp32 stores), so the maps agree to the last bit
+        assert np.array_equal(dev, host), (name, np.abs(dev - host).max())
+
+
+def test_device_squad_formation_equals_host_walk(models):
+    """cotr_group_tasks (form_squad for a whole batch in one device call) against the host walk of the reference's
+    form_grouped_batch: same squads, same member order -> identical correspondences, with and without the
+    stranded-task fix, for a load small enough that squads fill up (max_load) and large enough that they do not."""
+    from cotr_b200.inference.sparse_engine import FasterSparseEngine
+    from cotr_b200.utils.utils import fix_randomness
+    native, _ = models
+    img_a = synthetic_image(49, 400, 520)
+    img_b = synthetic_image(50, 460, 380)
+    rs = np.random.RandomState(21)
+    queries = np.stack([rs.uniform(5, 515, 90), rs.uniform(5, 395, 90)], axis=1)
+    zooms = np.linspace(0.5, 0.0625, 4)
+    for max_load, rescue in ((6, False), (64, True)):
+        results = []
+        for on_device in (True, False):
+            fix_randomness(0)
+            eng = FasterSparseEngine(native, 8, mode='tile', max_load=max_load, rescue_stranded=rescue, device_grouping=on_device)
+            results.append(eng.cotr_corr_multiscale(img_a, img_b, zooms, 1, max_corrs=90, queries_a=queries.copy(), force=True))
+        assert results[0].shape == results[1].shape and results[0].shape[0] > 3
+        assert np.array_equal(results[0], results[1])
+    # the kernel alone, against a direct numpy restatement of the walk
+    from cotr_b200 import capi
+    n = 3000
+    pts = rs.uniform(0, 100, (n, 4))
+    centre = rs.uniform(0, 100, (n, 4))
+    half = rs.uniform(2, 15, (n, 1))
+    boxes = np.stack([centre[:, 0] - half[:, 0], centre[:, 0] + half[:, 0], centre[:, 1] - half[:, 0], centre[:, 1] + half[:, 0],
+                      centre[:, 2] - 3 * half[:, 0], centre[:, 2] + 3 * half[:, 0], centre[:, 3] - 3 * half[:, 0], centre[:, 3] + 3 * half[:, 0]], axis=1)
+    squad, rank, n_squads = capi.group_tasks(pts, boxes, 32, 20, "cuda")
+    free = np.ones(n, dtype=bool)
+    ref_squad = -np.ones(n, dtype=np.int32); ref_rank = -np.ones(n, dtype=np.int32)
+    made = 0
+    for i in range(n):
+        if not free[i]:
+            continue
+        free[i] = False
+        ref_squad[i] = made; ref_rank[i] = 0
+        b = boxes[i]
+        fits = ((pts[:, 0] > b[0]) & (pts[:, 0] < b[1]) & (pts[:, 1] > b[2]) & (pts[:, 1] < b[3]) &
+                (pts[:, 2] > b[4]) & (pts[:, 2] < b[5]) & (pts[:, 3] > b[6]) & (pts[:, 3] < b[7]))
+        loads = np.where(fits & free)[0][:20]
+        ref_squad[loads] = made; ref_rank[loads] = 1 + np.arange(len(loads))
+        free[loads] = False
+        made += 1
+        if made >= 32:
+            break
+    assert n_squads == made and np.array_equal(squad, ref_squad) and np.array_equal(rank, ref_rank)

@@ -46,6 +46,7 @@ def build(rev, name):
 
 
 def one(path):
+    os.environ["COTR_B200_ALLOW_OLD_LIB"] = "1"
     import torch
     from cotr_b200 import capi
     capi.LIB_PATH = path

@@ -284,7 +284,7 @@ def launch_profile():
     model = build_model(None)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     model = model.cuda().eval()
-    img, q = fixtures.make_inputs(1, 1, 1024)
+    img, q = fixtures.make_inputs(1, int(os.environ.get("COTR_PROFILE_B", "1")), int(os.environ.get("COTR_PROFILE_Q", "1024")))
     img = torch.from_numpy(img).cuda(); q = torch.from_numpy(q).cuda()
     nat = model.native()
     for _ in range(3):
