@@ -114,7 +114,9 @@ struct EpiOperands {
     uint4 res_hi[2], res_lo[2];
 };
 
-template <int BN, bool LN, int MODE>
+// DLN: the instantiation carries the deferred-LayerNorm operands (GemmParams::a_ln_cs / res_ln_part / ln_part_out) and the
+// dataflow dependencies (GemmParams::sync).  The default schedule uses DLN = false kernels, which contain none of it.
+template <int BN, bool LN, int MODE, bool DLN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p, const int npad, long long* __restrict__ ts) {
     using C = Cfg<BN>;
     // debug timeline (ts != null): slot layout documented in tools/bringup.py::gemm_timeline
@@ -133,13 +135,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
     uint64_t* vec_full = bars + 3 * C::kStages + 2;        // deferred LayerNorm: the per-column vectors are staged
     uint64_t* dep_ready = bars + 3 * C::kStages + 3;       // dataflow mode: the polling thread has seen the producer's counters
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 4);
-    const bool dflow = p.sync.dep_mode != DEP_PDL;         // counters in global memory instead of griddepcontrol.wait (common.cuh)
+    const bool dflow = DLN && p.sync.dep_mode != DEP_PDL;  // counters in global memory instead of griddepcontrol.wait (common.cuh)
     float* vec_a = reinterpret_cast<float*>(stage_base + C::kVecOffset);      // a_ln: column sums of W'; res_ln: gamma
     float* vec_b = vec_a + BN;                                                  //                         res_ln: beta
     float2* st_a = reinterpret_cast<float2*>(vec_b + BN);                       // (mean, rstd) of the A rows of this tile
     float2* st_r = st_a + BM;                                                   // (mean, rstd) of the residual rows
     // deferred LayerNorm (GemmParams::a_ln_cs / res_ln_part / ln_part_out): only the row-major loader instantiations carry it
-    constexpr bool kCanLnA = (MODE == LD_GATHER) && !LN;
+    static_assert(!DLN || (MODE == LD_GATHER && !LN), "deferred LayerNorm / dataflow: row-major operand tiles only");
+    constexpr bool kCanLnA = DLN;
     const bool has_aln = kCanLnA && p.a_ln_cs != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,8 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
         }
         mbar_init(accum_full, 1);
         mbar_init(part_full, 1);
-        mbar_init(vec_full, 64);
-        mbar_init(dep_ready, 1);
+        if (DLN) {
+            mbar_init(vec_full, 64);
+            mbar_init(dep_ready, 1);
+        }
         mbar_fence_init();
         if (ksplit > 1) mbar_arrive_expect_tx(part_full, (uint32_t)(ksplit - 1) * (uint32_t)(BM / ksplit) * C::kPartPitch);
     }
@@ -750,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 
     tcgen05_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) dep_signal_thread(p.sync, blockIdx.x);       // every store of this CTA precedes the barrier above
+    if (DLN && threadIdx.x == 0) dep_signal_thread(p.sync, blockIdx.x);       // every store of this CTA precedes the barrier above
     if (warp == 5) tmem_dealloc(tmem_base, C::kTmemCols);
     if (threadIdx.x == 160) COTR_TS(60);
     if (my_ts && threadIdx.x == 160) my_ts[62] = global_ns();
@@ -759,12 +764,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
 
 thread_local GemmLaunchInfo* g_launch_info = nullptr;       // where launch_one reports the grid it chose
 
-template <int BN, bool LN, int MODE>
+template <int BN, bool LN, int MODE, bool DLN = false>
 int launch_one(const GemmParams& p, cudaStream_t s) {
     using C = Cfg<BN>;
     static unsigned long long configured = 0;      // bit per device
     if (first_use_on_device(&configured)) {
-        COTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, LN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        COTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, LN, MODE, DLN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(C::kSmemBytes + C::kPartMaxBytes)));
     }
     const int npad = tc_npad(p.N);
@@ -780,22 +785,29 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
             else if (C::kMaxSplit >= 2 && kc % 2 == 0 && ctas * 2 <= 160) ksplit = 2;
         }
     }
-    COTR_CHECK(p.a_ln_cs == nullptr || (MODE == LD_GATHER && !LN && p.K == 256 && p.a_mode == A_ROWMAJOR && p.a_ln_part != nullptr),
+    COTR_CHECK(p.a_ln_cs == nullptr || (DLN && p.K == 256 && p.a_mode == A_ROWMAJOR && p.a_ln_part != nullptr),
                "gemm_tc: the deferred LayerNorm on A needs a row-major operand with K = 256 and its partial statistics");
-    COTR_CHECK((p.res_ln_part == nullptr && p.ln_part_out == nullptr) || (MODE == LD_GATHER && !LN),
+    COTR_CHECK((p.res_ln_part == nullptr && p.ln_part_out == nullptr && p.sync.dep_mode == DEP_PDL && p.sync.sig == nullptr) || DLN,
                "gemm_tc: deferred-LayerNorm residual / statistics on an unsupported tile");
     COTR_CHECK(p.ln_part_out == nullptr || (p.N == 256 && !p.remap && p.out_f32 == nullptr), "gemm_tc: row statistics need a plain N = 256 output");
     grid.z = ksplit;
     const size_t smem = C::kSmemBytes + (size_t)(ksplit - 1) * (BM / ksplit) * C::kPartPitch;     // incoming partial rows
     if (g_launch_info) *g_launch_info = GemmLaunchInfo{(int)grid.x, (int)grid.y, ksplit};
-    COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE>, grid, dim3(kThreads), smem, s, ksplit, p, npad, next_trace_block()));
+    COTR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<BN, LN, MODE, DLN>, grid, dim3(kThreads), smem, s, ksplit, p, npad, next_trace_block()));
     return 0;
 }
 
 template <int BN, bool LN>
 int launch_mode(const GemmParams& p, cudaStream_t s) {
     const bool gather = (p.a_mode == A_ROWMAJOR || p.a_mode == A_TOKENS);
-    if (gather && (p.K & 7) == 0 && (p.lda & 7) == 0) return launch_one<BN, LN, LD_GATHER>(p, s);
+    if (gather && (p.K & 7) == 0 && (p.lda & 7) == 0) {
+        if constexpr (!LN) {
+            const bool dln = p.a_ln_cs != nullptr || p.res_ln_part != nullptr || p.ln_part_out != nullptr ||
+                             p.sync.dep_mode != DEP_PDL || p.sync.sig != nullptr;
+            if (dln) return launch_one<BN, LN, LD_GATHER, true>(p, s);
+        }
+        return launch_one<BN, LN, LD_GATHER>(p, s);
+    }
     if constexpr (!LN && BN >= 32) {
         if (p.a_mode == A_CONV_NHWC && (p.C & 63) == 0) return launch_one<BN, LN, LD_CONV>(p, s);
     }

@@ -50,6 +50,8 @@ struct DevLinear {
     // cs its column sums and b_tc = beta W^T + b; w / b stay the checkpoint's values for the fp32 SIMT path.
     float* cs = nullptr;
     float* b_tc = nullptr;
+    void* wtc_plain = nullptr;       // tensor-core image of the un-folded W (explicit-LayerNorm schedule on the tensor-core path)
+    float wtc_plain_scale = 1.f;
 };
 
 struct Block {
@@ -221,6 +223,7 @@ int make_linear_ln(cotr_model* m, const std::vector<float>& w, const std::vector
         cb[n] = (float)c;
     }
     if (upload_tc(m, wg, N, K, &out->wtc, &out->wtc_scale)) return 1;
+    if (upload_tc(m, w, N, K, &out->wtc_plain, &out->wtc_plain_scale)) return 1;
     if (upload(m, cs, &out->cs) || upload(m, cb, &out->b_tc)) return 1;
     if (folded_bias) *folded_bias = cb;
     return 0;
@@ -378,12 +381,16 @@ GemmParams gemm_base(int M, int N, int K, CSplit16 A, int lda, const float* W, c
 // One tcgen05 GEMM launch with its dataflow bookkeeping.  dep_mode: DEP_ALL / DEP_TILE (the A rows of a CTA's tile come
 // from the same 128-row tile of the previous launch, and nothing this launch overwrites is still read by other tiles).
 int launch_tc(const Run& r, GemmParams& p, int dep_mode = DEP_ALL) {
-    p.sync = plan_dep(r, dep_mode, p.M);
+    // only the row-major operand kernels exist in a dataflow-capable form (gemm_tc.cu, DLN instantiations): convolutions
+    // keep the hardware wait and announce nothing, so their successor falls back to the hardware wait as well
+    const bool flow_ok = (p.a_mode == A_ROWMAJOR || p.a_mode == A_TOKENS) && (p.K & 7) == 0 && (p.lda & 7) == 0;
+    if (flow_ok) p.sync = plan_dep(r, dep_mode, p.M);
+    else if (r.sp) r.sp->prev = nullptr;
     p.sync.sig_tiles = p.sync.sig ? sync_tiles_for(p.M) : 0;
     GemmLaunchInfo info{0, 0, 1};
     LaunchScope scope(r, K_GEMM_TC, p.M, p.N, p.K);
     if (launch_gemm_tc(p, r.s, &info)) return 1;
-    plan_done(r, p.sync, info.row_tiles * info.col_tiles * info.ksplit, info.col_tiles * info.ksplit, p.M);
+    if (flow_ok) plan_done(r, p.sync, info.row_tiles * info.col_tiles * info.ksplit, info.col_tiles * info.ksplit, p.M);
     return 0;
 }
 
@@ -430,7 +437,8 @@ int run_gemm(const Run& r, GemmParams p, float* ln_scratch, int dep_mode = DEP_A
 int run_linear(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda, Split16 out, int ldc, bool relu,
                CSplit16 residual = CSplit16{nullptr, nullptr}, int ldr = 0, const float* ln_g = nullptr,
                const float* ln_b = nullptr, float* ln_scratch = nullptr, int dep_mode = DEP_ALL) {
-    GemmParams p = gemm_base(M, L.n, L.k, A, lda, L.w, L.wtc, L.wtc_scale, out, ldc);
+    // explicit-LayerNorm schedule: layers that also exist in a gamma-folded form use their plain image here
+    GemmParams p = gemm_base(M, L.n, L.k, A, lda, L.w, L.wtc_plain ? L.wtc_plain : L.wtc, L.wtc_plain ? L.wtc_plain_scale : L.wtc_scale, out, ldc);
     p.bias = L.b;
     p.relu = relu ? 1 : 0;
     p.res = residual; p.ldr = ldr;
@@ -539,7 +547,21 @@ int ensure_sync_ctr(cotr_model* m) {
     return 0;
 }
 // bring-up switch: cotr_debug_set_variant bit 18 turns the dataflow dependencies off (hardware griddepcontrol.wait everywhere)
-inline bool dataflow_enabled(const cotr_model* m) { return m->gemm_path == 0 && !(g_tc_variant & (1 << 18)) && g_use_pdl; }
+// Schedule selection (profiles/r02_deferred_layernorm.md has the measurements behind it).
+// Deferred LayerNorm (no LayerNorm launches; consumers normalise on the fly) removes 12 launches from the encoder and
+// 12 from each decoder chunk but makes its consumer GEMMs a little longer: on B200 it loses 2.4% on the 512-token /
+// 1024-row chains of the headline shape and wins 3-5% once a section has thousands of rows, so each section picks it
+// by its row count.  cotr_debug_set_variant overrides: bit 19 = always deferred, bit 16 = never.  Bits 19 + 18 together
+// additionally swap griddepcontrol.wait for the counter-based dataflow dependencies of common.cuh - measured slower
+// everywhere, opt-in only.
+constexpr int kDeferredLnMinRows = 2048;
+inline bool deferred_ln_enabled(const cotr_model* m, int rows) {
+    if (m->gemm_path != 0 || (g_tc_variant & (1 << 16))) return false;
+    return (g_tc_variant & (1 << 19)) != 0 || rows >= kDeferredLnMinRows;
+}
+inline bool dataflow_enabled(const cotr_model* m) {
+    return m->gemm_path == 0 && (g_tc_variant & (1 << 18)) != 0 && (g_tc_variant & (1 << 19)) != 0 && !(g_tc_variant & (1 << 16)) && g_use_pdl;
+}
 
 // Captured graphs embed workspace / staging / context addresses: whenever one of those is reallocated every graph is
 // stale.  The shapes stay "seen", so the next call of each shape re-captures against the new buffers.
@@ -672,7 +694,7 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
     // transformer.py:143-159 x6 (post-LN).  q = k = x + pos is folded into the constant add_qkv matrix.
     // q | k land row-major in qk [T][512]; v lands transposed in vt [pair][256][512] (what P V needs as its B operand).
     Split16 xin = w.src;      // layer input
-    if (m->gemm_path == 0) {
+    if (deferred_ln_enabled(m, T)) {
         // Tensor-core path: no LayerNorm kernel and no LayerNorm epilogue.  A LayerNorm output is never stored; its
         // producer writes the pre-norm rows (xa: x + attention, xb: x1 + FFN) and every consumer applies the norm on
         // the fly (GemmParams::a_ln_cs for GEMM inputs, res_ln_part for residual operands) from the partial row
@@ -693,7 +715,7 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
                 if (ln_in) { p.a_ln_cs = e.qkv.cs; p.a_ln_part = w.enc_st_b; }
                 if (launch_tc(r, p, DEP_TILE)) return 1;
             }
-            AttnParams a;
+            AttnParams a{};
             a.q = cs(qk_l); a.ldq = 2 * kDModel;
             a.k = offset(cs(qk_l), kDModel); a.ldk = 2 * kDModel;
             a.vt = cs(vt_l); a.vt_pair_stride = kVtLayer;
@@ -729,20 +751,20 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
         m->last_pairs = B;
         return 0;
     }
-    // fp32 SIMT cross-check path: explicit LayerNorm launches, the checkpoint's weights as they are
+    // default schedule (and the fp32 SIMT cross-check path): explicit LayerNorm launches, the checkpoint's weights as they are
     m->last_mem_pre_ln = false;
     const int n_enc_dbg = (g_tc_variant >> 20) & 7;
     for (int l = 0; l < (n_enc_dbg ? n_enc_dbg : kEncLayers); ++l) {
         const EncLayer& e = m->enc[l];
         {
-            GemmParams p = gemm_base(T, 3 * kDModel, kDModel, cs(xin), kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, w.qk, 2 * kDModel);
+            GemmParams p = gemm_base(T, 3 * kDModel, kDModel, cs(xin), kDModel, e.qkv.w, e.qkv.wtc_plain ? e.qkv.wtc_plain : e.qkv.wtc, e.qkv.wtc_plain ? e.qkv.wtc_plain_scale : e.qkv.wtc_scale, w.qk, 2 * kDModel);
             p.addmat = e.add_qkv; p.add_period = kTokens; p.ld_add = 3 * kDModel;
             p.remap = 1;
             p.blk_map[0] = 0; p.blk_map[1] = kDModel; p.blk_map[2] = -1;
             p.vt = w.vt; p.n_vt = 1;
             if (run_gemm(r, p, nullptr)) return 1;
         }
-        AttnParams a;
+        AttnParams a{};
         a.q = cs(w.qk); a.ldq = 2 * kDModel;
         a.k = offset(cs(w.qk), kDModel); a.ldk = 2 * kDModel;
         a.vt = cs(w.vt); a.vt_pair_stride = kVtLayer;
@@ -761,7 +783,7 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
     // transformer.py:192-195: K_l = (mem + pos) Wk_l^T + bk_l, V_l = mem Wv_l^T + bv_l for all 6 decoder layers in ONE
     // GEMM (N = 3072): K blocks go row-major into ctx->k [T][1536], V blocks transposed into ctx->vt [pair][6][256][512].
     {
-        GemmParams p = gemm_base(T, 2 * kKCols, kDModel, cs(xin), kDModel, m->kv_all.w, m->kv_all.wtc, m->kv_all.wtc_scale, ctx->k, kKCols);
+        GemmParams p = gemm_base(T, 2 * kKCols, kDModel, cs(xin), kDModel, m->kv_all.w, m->kv_all.wtc_plain ? m->kv_all.wtc_plain : m->kv_all.wtc, m->kv_all.wtc_plain ? m->kv_all.wtc_plain_scale : m->kv_all.wtc_scale, ctx->k, kKCols);
         p.addmat = m->add_kv; p.add_period = kTokens; p.ld_add = 2 * kKCols;
         p.remap = 1;
         for (int l = 0; l < kDecLayers; ++l) {
@@ -800,7 +822,7 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
     // all 6 layers is one GEMM.
     if (run_linear(r, m->qpos_all, R, cs(w.qpos), kDModel, w.qp, kQpCols, false, none, 0, nullptr, nullptr, nullptr, DEP_TILE)) return 1;
 
-    if (m->gemm_path == 0) {
+    if (deferred_ln_enabled(m, R)) {
         // Tensor-core path with deferred LayerNorms (see encode_impl): w.t = t + attention (norm2 deferred),
         // w.t2 = t1 + FFN (norm3 deferred); dec_st_a = partial row statistics of w.t (norm2), dec_st_b of w.t2 (norm3).
         for (int l = 0; l < kDecLayers; ++l) {
@@ -813,7 +835,7 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
                                    offset(cs(w.qp), (size_t)l * kDModel), kQpCols)) return 1;
                 q = cs(w.qb); ldq = kDModel;
             }
-            AttnParams a;
+            AttnParams a{};
             a.q = q; a.ldq = ldq;
             a.k = offset(cs(ctx->k), (size_t)l * kDModel); a.ldk = kKCols;
             a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
@@ -846,7 +868,7 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
                 if (run_linear(r, d.q, R, cs(w.t), kDModel, w.qb, kDModel, false, offset(cs(w.qp), (size_t)l * kDModel), kQpCols)) return 1;
                 q = cs(w.qb); ldq = kDModel;
             }
-            AttnParams a;
+            AttnParams a{};
             a.q = q; a.ldq = ldq;
             a.k = offset(cs(ctx->k), (size_t)l * kDModel); a.ldk = kKCols;
             a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
@@ -1606,7 +1628,7 @@ int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const 
         cudaFree(ed);
         if (rc) return rc;
     }
-    AttnParams a;
+    AttnParams a{};
     a.q = cs(q16.t); a.ldq = kDModel; a.k = cs(k16.t); a.ldk = kDModel;
     a.vt = cs(vt16.t); a.vt_pair_stride = kVtLayer;
     a.out = o16.t; a.ldo = kDModel; a.nq = nq; a.npairs = npairs; a.pair0 = 0;

@@ -185,7 +185,10 @@ int cotr_test_attention(int path, const float* q_dev, const float* k_dev, const 
                         int nq, int npairs);
 /* bring-up / A-B switches (0 = production): bit 8 (256) disables programmatic dependent launch, bit 9 (512) disables
  * split-K, bits 10-11 / 12-13 move the CTA-count thresholds of the 64- / 128-wide GEMM tiles, bits 14-15 lower the
- * minimum K of split-K (16 >> n chunks of 64), bit 17 selects trace mode for cotr_debug_set_timestamps.
+ * minimum K of split-K (16 >> n chunks of 64), bit 17 selects trace mode for cotr_debug_set_timestamps, bits 20-22 stop
+ * the encoder after n layers.  Schedule: by default a transformer section with >= 2048 rows runs the deferred-LayerNorm
+ * schedule (no LayerNorm launches), smaller ones the explicit one; bit 19 forces deferred everywhere, bit 16 never;
+ * bits 19 + 18 add the counter-based dataflow dependencies (experimental, slower - profiles/r02_deferred_layernorm.md).
  * Process-wide; graphs captured under another value are NOT dropped (call cotr_set_gemm_path twice to drop them). */
 void cotr_debug_set_variant(int variant);
 /* debug timeline of the tcgen05 kernels: DEVICE buffer of 64 int64 per CTA receiving clock64() deltas of the pipeline

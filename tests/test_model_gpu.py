@@ -180,3 +180,27 @@ def test_graph_replay_survives_workspace_growth(built_lib):
     assert torch.equal(m(t1, u1)["pred_corrs"], first)
     assert torch.equal(m(t4, u4)["pred_corrs"], big[0])
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("variant,name", [(1 << 19, "deferred-layernorm"), ((1 << 19) | (1 << 18), "deferred-layernorm+dataflow"),
+                                          (1 << 16, "explicit-layernorm")])
+def test_experimental_schedules_match_the_reference(golden_dir, built_lib, variant, name):
+    """The schedules cotr_debug_set_variant can force (bit 19: LayerNorms applied on the fly by their consumers from
+    partial row statistics, everywhere; bits 19 + 18: launch-to-launch dependencies through counters in global memory
+    instead of griddepcontrol.wait; bit 16: explicit LayerNorm launches everywhere - by default each section picks by
+    its row count, profiles/r02_deferred_layernorm.md) all stay correct: same goldens, same tolerance, eager and
+    graph-replayed, also for a batch whose query count is not a tile multiple."""
+    from cotr_b200 import capi
+    capi.lib().cotr_debug_set_variant(variant)
+    try:
+        for case in ("model_b1_q1024", "model_b2_q100", "model_b16_q1024"):
+            g, sd, img, queries, q_stride = _case(golden_dir, case)
+            model = _build(sd)
+            t, q = torch.from_numpy(img).cuda(), torch.from_numpy(queries).cuda()
+            for rep in range(3):                                   # eager, capture, replay
+                pred = model(t, q)["pred_corrs"].cpu().numpy()[:, ::q_stride]
+                assert np.abs(pred - g["ref_pred_fp64"]).max() < TOL_INTERNAL, (case, rep)
+            if case == "model_b1_q1024":
+                assert model.native().last_launch_count() == (135 if variant == (1 << 16) else 111)
+    finally:
+        capi.lib().cotr_debug_set_variant(0)

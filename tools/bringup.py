@@ -234,7 +234,7 @@ def forward_trace():
     img = torch.from_numpy(img).cuda(); q = torch.from_numpy(q).cuda()
     n_launch = int(os.environ.get("COTR_TRACE_N", "112"))
     ts = torch.zeros(n_launch * 256 * 64, dtype=torch.int64, device="cuda")
-    capi.lib().cotr_debug_set_variant(1 << 17)
+    capi.lib().cotr_debug_set_variant((1 << 17) | int(os.environ.get("COTR_TRACE_VARIANT", "0")))
     for rep in range(4):                      # eager, capture, replay, replay
         capi.lib().cotr_debug_set_timestamps(ctypes.c_void_p(ts.data_ptr()))
         model(img, q)
@@ -269,6 +269,11 @@ def forward_trace():
             if ctas[c, 61] > 0 and (c < 6 or c % 16 == 0):
                 print(f"    launch {i} cta {c:3d}: start {(ctas[c, 61].item() - t0) / 1e3:8.2f} wait done {(ctas[c, 61].item() + ctas[c, 2].item() / 1.965 - t0) / 1e3:8.2f} "
                       f"end {(ctas[c, 62].item() - t0) / 1e3:8.2f}   cycles: setup {ctas[c, 1].item()} wait {ctas[c, 2].item()} end {ctas[c, 60].item()}", flush=True)
+    for i in [int(x) for x in os.environ.get("COTR_TRACE_SLOTS", "").split(",") if x]:
+        for c in (0, 1, 9):
+            r = t[i][c].tolist()
+            if r[62] > 0:
+                print(f"    launch {i} cta {c} cycle stamps: " + " ".join(f"{k}:{r[k]}" for k in range(1, 61) if r[k] > 0), flush=True)
     for (i, n, start, waited, end0, end) in rows:
         gap = "" if prev_end is None else f" gap after prev end {start - prev_end:+6.2f}"
         print(f"  launch {i:3d} ctas {n:3d}: first CTA start {start:8.2f}  cta0 wait done {waited:8.2f}  cta0 end {end0:8.2f}  last CTA end {end:8.2f} us{gap}", flush=True)
