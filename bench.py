@@ -80,6 +80,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def samples(self):
+        return len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -299,12 +302,12 @@ def run_native(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     nat = model.native()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # nvidia-smi needs ~1 s to deliver its first sample: start it before the warm-up
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
 
     # ---- value: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps ----------
     dev_ms = _timed_steps(step, flush, args.steps, barrier)
@@ -337,7 +340,6 @@ def run_native(args, rank, local_rank, world):
         e2e_times.append(time.perf_counter() - t0)
     barrier()
     e2e_ms = float(np.mean(e2e_times)) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- BASELINE.json configs[3] per GPU: 8 pairs x 1024 queries in one forward (64 pairs over 8 GPUs) --------------
     B4 = 8
@@ -355,6 +357,17 @@ def run_native(args, rank, local_rank, world):
     c4_steps = max(5, min(args.steps, 20))
     c4_ms = _timed_steps(step4, flush, c4_steps, barrier)
     c4_launches = nat.last_launch_count()
+    # The timed regions above last ~0.1 s in total - shorter than nvidia-smi's 200 ms sampling period.  Keep the same step
+    # loop running (untimed) until at least 5 samples under load exist, so the clock record describes this workload.
+    clocks = None
+    if rank == 0:
+        t_end = time.perf_counter() + 6.0
+        while sampler.proc is not None and sampler.samples() < 5 and time.perf_counter() < t_end:
+            for _ in range(50):
+                model(img, queries)
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["note"] = "sampled every 200 ms from before the warm-up to after the timed regions; the step loop is continued untimed until >= 5 samples exist"
 
     # ---- kernel shares: per-launch events (library profiler, eager launches), rank 0 ---------------------------------
     per_kernel = {}

@@ -442,11 +442,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                 for (int j = 0; j < 4; ++j) o.add[j] = __ldg(reinterpret_cast<const float4*>(add_row + nb) + j);
             }
             if (has_res) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    o.res_hi[j] = __ldcg(reinterpret_cast<const uint4*>(p.res.hi + res_off + nb) + j);
-                    o.res_lo[j] = __ldcg(reinterpret_cast<const uint4*>(p.res.lo + res_off + nb) + j);
-                }
+                // 16 halves of one plane = one 32-byte sector: a single 256-bit ld.global.cg per plane (two 128-bit
+                // loads would be two L2 requests for the same sector - activations bypass L1, see load8_split)
+                ld_cg_256(p.res.hi + res_off + nb, o.res_hi[0], o.res_hi[1]);
+                ld_cg_256(p.res.lo + res_off + nb, o.res_lo[0], o.res_lo[1]);
             }
         };
         auto apply = [&](const EpiOperands& o, float (&v)[16], int nb) {
@@ -900,7 +899,8 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s, GemmLaunchInfo* info) {
     COTR_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "gemm_tc: empty problem %d x %d x %d", p.M, p.N, p.K);
     COTR_CHECK(p.Wtc != nullptr, "gemm_tc: weight has no tensor-core image");
     COTR_CHECK(p.out_f32 != nullptr || (p.N & 15) == 0, "gemm_tc: split16 outputs need N %% 16 == 0 (N=%d)", p.N);
-    COTR_CHECK(p.res.hi == nullptr || ((p.ldr & 7) == 0 && (p.N & 15) == 0), "gemm_tc: residual needs ldr %% 8 == 0");
+    COTR_CHECK(p.res.hi == nullptr || ((p.ldr & 15) == 0 && (p.N & 15) == 0 && ((uintptr_t)p.res.hi & 31) == 0 && ((uintptr_t)p.res.lo & 31) == 0),
+               "gemm_tc: residual needs ldr %% 16 == 0 and 32-byte aligned planes");
     COTR_CHECK(p.addmat == nullptr || ((p.ld_add & 3) == 0 && (p.N & 15) == 0), "gemm_tc: add-matrix needs ld %% 4 == 0");
     COTR_CHECK(p.out_f32 != nullptr || (p.ldc & 7) == 0, "gemm_tc: split16 output needs ldc %% 8 == 0");
     if (p.ln_gamma) {

@@ -46,6 +46,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- 256-bit global load through L2 only (LDG.E.ENL2.256): 32-byte aligned address --------------------------------
+__device__ __forceinline__ void ld_cg_256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+
 // ---- cp.async (LDGSTS): 16 bytes global -> shared, zero-filled when src_bytes == 0 --------------------------------
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_b13_bench_n1.json 2> gpurun_out/r02_b13_bench_n1.err
+timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/r02_b13_bench_ref.json 2> gpurun_out/r02_b13_bench_ref.err
+timeout 900 python bench.py --config 3 --steps 1 > gpurun_out/r02_b13_config3.json 2> gpurun_out/r02_b13_config3.err
+timeout 600 python bench.py --config 5 --steps 1 > gpurun_out/r02_b13_config5.json 2> gpurun_out/r02_b13_config5.err
+timeout 300 python __graft_entry__.py smoke > gpurun_out/r02_b13_smoke.log 2>&1
+for f in bench_n1 bench_ref config3 config5; do echo "== $f"; tail -c 2500 gpurun_out/r02_b13_$f.json; tail -3 gpurun_out/r02_b13_$f.err; done; tail -2 gpurun_out/r02_b13_smoke.log
