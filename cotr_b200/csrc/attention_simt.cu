@@ -37,9 +37,16 @@ __global__ void __launch_bounds__(kWarps * 32) attention_simt_kernel(const AttnP
     const size_t kv_row0 = (size_t)(p.pair0 + pair_local) * kTokens;
     if (tid == 0) pdl_launch_dependents();
     pdl_wait();
+    // keys / values either row-major / transposed (fp32 SIMT schedule) or as the attention operand images the
+    // tensor-core schedule writes (common.cuh kAttnHeadImgBytes) - this kernel also serves its launches with < 32 query rows
+    const unsigned char* img = p.kv_img ? p.kv_img + (size_t)(p.pair0 + pair_local) * p.img_pair_stride + (size_t)head * kAttnHeadImgBytes : nullptr;
     for (int idx = tid; idx < kTokens * (kHeadDim / 8); idx += blockDim.x) {        // K rows: 8 elements per step
         const int key = idx >> 2, d8 = (idx & 3) * 8;
         float v[8];
+        if (img) {
+            const CSplit16 kimg{reinterpret_cast<const __half*>(img), reinterpret_cast<const __half*>(img + kAttnKPlaneBytes)};
+            load8_split(kimg, ((size_t)(d8 >> 3) * kTokens + key) * 8, v);
+        } else
         load8_split(p.k, (kv_row0 + key) * p.ldk + head * kHeadDim + d8, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) Ks[key * kKStride + d8 + j] = v[j];
@@ -48,6 +55,11 @@ __global__ void __launch_bounds__(kWarps * 32) attention_simt_kernel(const AttnP
     for (int idx = tid; idx < kHeadDim * (kTokens / 8); idx += blockDim.x) {        // V^T rows: 8 keys per step
         const int d = idx >> 6, k8 = (idx & 63) * 8;
         float v[8];
+        if (img) {
+            const unsigned char* g = img + kAttnKImgBytes + (size_t)(k8 >> 3) * kAttnVGroupBytes + (size_t)d * 16;
+            const CSplit16 vimg{reinterpret_cast<const __half*>(g), reinterpret_cast<const __half*>(g + kHeadDim * 16)};
+            load8_split(vimg, 0, v);
+        } else
         load8_split(p.vt, vbase + (size_t)d * kTokens + k8, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) Vs[(k8 + j) * kHeadDim + d] = v[j];

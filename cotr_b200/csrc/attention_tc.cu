@@ -50,6 +50,9 @@ constexpr uint32_t kOffStat = kOffP + 4 * kPPlane;         // row max / row sum 
 constexpr uint32_t kOffBar = kOffStat + 2 * kTile * 4;
 constexpr uint32_t kSmemBytes = kOffBar + 128;
 static_assert(kSmemBytes <= 227 * 1024, "attention tile does not fit shared memory");
+// the operand images of common.cuh are byte-for-byte these shared-memory tiles
+static_assert(2 * kKPlane == kAttnKImgBytes && kKPlane == kAttnKPlaneBytes && kVLbo == kAttnVGroupBytes && kVBytes == kAttnVImgBytes &&
+              kOffV == kOffK + kAttnKImgBytes, "attention operand images and shared-memory tiles went out of step");
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -71,7 +74,9 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
     uint64_t* p_full = bars + 4;     // [2]
     uint64_t* p_empty = bars + 6;    // [2]
     uint64_t* dep_ready = bars + 8;  // dataflow mode (common.cuh LaunchSync): the polling thread has seen the producer's counters
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* k_img_full = bars + 9; // operand images: the bulk copy of K (hi + lo planes) has landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+    const bool img = p.kv_img != nullptr;       // keys / values arrive as operand images by bulk TMA (tensor-core schedule)
     const bool dflow = p.sync.dep_mode != DEP_PDL;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
 
     if (threadIdx.x == 0) {
         mbar_init(qk_full, kSoftmaxThreads);
-        mbar_init(v_full, kSoftmaxThreads);
+        mbar_init(v_full, img ? 1 : kSoftmaxThreads);
         mbar_init(s_full, 1);
         mbar_init(o_full, 1);
         mbar_init(&p_full[0], kSoftmaxThreads);
@@ -90,6 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         mbar_init(&p_empty[0], 1);
         mbar_init(&p_empty[1], 1);
         mbar_init(dep_ready, 1);
+        mbar_init(k_img_full, 1);
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc(tmem_ptr, 512);
@@ -116,6 +122,15 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
         if (dflow) mbar_wait(dep_ready, 0); else pdl_wait();      // prologue above overlaps the previous kernel
         if (t == 0) COTR_TS(2);
 
+        if (img && t == 0) {
+            // keys and values of this (pair, head): two bulk-TMA copies (UBLKCP) of the operand images straight into the
+            // tiles, issued by one thread before anything else; the 256 threads then only stage the 16 KB of Q
+            const unsigned char* src = p.kv_img + (size_t)(p.pair0 + pair_local) * p.img_pair_stride + (size_t)head * kAttnHeadImgBytes;
+            mbar_arrive_expect_tx(k_img_full, (uint32_t)kAttnKImgBytes);
+            tma_bulk_g2s(smem + kOffK, src, (uint32_t)kAttnKImgBytes, k_img_full);
+            mbar_arrive_expect_tx(v_full, (uint32_t)kAttnVImgBytes);
+            tma_bulk_g2s(smem + kOffV, src + kAttnKImgBytes, (uint32_t)kAttnVImgBytes, v_full);
+        }
         // ---- stage Q (row t % 128, two of the four 16-byte K groups per thread) and K (4 keys per thread) --------
         {
             const int r = t & 127, kg0 = (t >> 7) * 2;
@@ -130,6 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                 cp_async16(dst, p.q.hi + qoff + kg * 8, bytes);
                 cp_async16(dst + kQPlane, p.q.lo + qoff + kg * 8, bytes);
             }
+            if (!img) {
 #pragma unroll
             for (int i = 0; i < kTokens / 128; ++i) {
                 const int key = r + 128 * i;
@@ -142,11 +158,12 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                     cp_async16(dst + kKPlane, p.k.lo + koff + kg * 8, 16u);
                 }
             }
+            }
         }
         cp_async_mbar_arrive_noinc(qk_full);
 
         // ---- stage V^T (already transposed in HBM): piece (key-group kg8, d) = 8 consecutive keys of row d ----
-        {
+        if (!img) {
             const size_t vbase = (size_t)(p.pair0 + pair_local) * p.vt_pair_stride + (size_t)head * kHeadDim * kTokens;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -157,8 +174,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
                 cp_async16(dst, p.vt.hi + voff, 16u);
                 cp_async16(dst + kVLoOff, p.vt.lo + voff, 16u);
             }
+            cp_async_mbar_arrive_noinc(v_full);
         }
-        cp_async_mbar_arrive_noinc(v_full);
         if (t == 0) COTR_TS(3);
 
         // ---- softmax out of TMEM ---------------------------------------------------------------------------
@@ -265,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const AttnPar
             constexpr uint32_t idesc_o2 = make_idesc_f16_f32(128, 2 * kHeadDim);
             const uint32_t hi_word = desc_hi(kSbo);
             mbar_wait(qk_full, 0);
+            if (img) mbar_wait(k_img_full, 0);
             tcgen05_fence_after();
             COTR_TS(20);
 #pragma unroll

@@ -181,6 +181,18 @@ constexpr int kFF = 1024;
 constexpr int kEncLayers = 6;
 constexpr int kDecLayers = 6;
 
+// Attention operand images (tensor-core path).  The keys and values of one (pair, slot, head) - slot = decoder layer, or 0
+// for the encoder's own layer - are stored in HBM exactly as the attention kernel wants them in shared memory, so that
+// staging them is two bulk-TMA copies issued by one thread (cp.async.bulk -> UBLKCP) instead of 8 192 16-byte cp.async:
+//   K image  [plane hi | lo][4 groups of 8 head dims][512 keys][16 B]           = 2 x 32 KB  (UMMA K-major canonical layout)
+//   V image  [64 groups of 8 keys][hi: 32 head dims x 16 B | lo: 32 x 16 B | 16 B pad]  = 64 x 1040 B
+// written in that form by the epilogue of the projection GEMM (split16.cuh::store16).
+constexpr size_t kAttnKPlaneBytes = 4 * 512 * 16;                         // 32 KB
+constexpr size_t kAttnKImgBytes = 2 * kAttnKPlaneBytes;                   // 64 KB
+constexpr size_t kAttnVGroupBytes = 2 * 32 * 16 + 16;                     // 1040 B
+constexpr size_t kAttnVImgBytes = 64 * kAttnVGroupBytes;                  // 66 560 B
+constexpr size_t kAttnHeadImgBytes = kAttnKImgBytes + kAttnVImgBytes;     // 132 096 B per (pair, slot, head)
+
 // ---------------------------------------------------------------------------------------------------------------
 // "split16" activations.  Every activation between kernels is stored as TWO fp16 planes, x ~= hi + lo (22 mantissa
 // bits, same bytes as fp32): the tensor-core kernels need their operands in exactly that form (gemm_tc.cu), so the
@@ -254,10 +266,14 @@ struct GemmParams {
     // stored at column offset blk_map[b] of `out`; blk_map[b] = -(v+1) -> the block is a value projection and is
     // stored TRANSPOSED as vt[((pair * n_vt + v) * 256 + c) * 512 + key] (row = pair*512 + key), the K-major B operand
     // the attention kernels need.
+    // With kv_img set (tensor-core path) the key / value blocks go into the attention operand images instead:
+    // blk_map[b] = -(v+1) -> value block of slot v, blk_map[b] = -1000 - s -> key block of slot s; the image of
+    // (pair, slot, head) starts at kv_img + ((pair * n_vt + slot) * 8 + head) * kAttnHeadImgBytes.
     int remap;
     int blk_map[12];
     Split16 vt;
     int n_vt;
+    unsigned char* kv_img;
 };
 
 // softmax(q k^T) v per head; q already carries the head_dim^-0.5 scale.
@@ -266,6 +282,10 @@ struct AttnParams {
     CSplit16 k; int ldk;         // rows: (pair0 + pair_local) * 512 + key
     CSplit16 vt;                 // [(pair0 + pair_local) * vt_pair_stride + (head*32 + d) * 512 + key]
     size_t vt_pair_stride;
+    // tensor-core path: keys and values as operand images (see kAttnHeadImgBytes); k / vt above are then unused.
+    // image of (pair0 + pair_local, head) = kv_img + (pair0 + pair_local) * img_pair_stride + head * kAttnHeadImgBytes
+    const unsigned char* kv_img;
+    size_t img_pair_stride;
     Split16 out; int ldo;
     int nq;                      // query rows per pair in this launch
     int npairs;

@@ -84,6 +84,7 @@ struct Workspace {
     // encoder
     Split16 src = kNoSplit, xa = kNoSplit, xb = kNoSplit, qk = kNoSplit, vt = kNoSplit, ao = kNoSplit, ffh = kNoSplit;
     Split16 qk2 = kNoSplit, vt2 = kNoSplit;      // odd encoder layers: with tile-level dependencies layer l+1 projects while layer l still attends
+    unsigned char *kvimg = nullptr, *kvimg2 = nullptr;      // [pairs][8 heads] attention operand images of the encoder's own k / v
     int* sync_ctr = nullptr;      // dataflow counter blocks (common.cuh LaunchSync): kSyncBlocks x kSyncBlockInts ints
     float* ln_tmp = nullptr;      // fp32 [tokens][256]: pre-LayerNorm rows of the SIMT cross-check path
     float2 *enc_st_a = nullptr, *enc_st_b = nullptr;     // [tokens][16] partial row statistics of xa / xb (deferred LayerNorms)
@@ -104,6 +105,8 @@ struct cotr_context {
     cotr_model* model = nullptr;
     cotr::Split16 k = cotr::kNoSplit;    // [max_pairs * 512][6 * 256]
     cotr::Split16 vt = cotr::kNoSplit;   // [max_pairs][6][256][512]  (value projections stored transposed)
+    unsigned char* img = nullptr;        // [max_pairs][6][8 heads] attention operand images (common.cuh kAttnHeadImgBytes)
+    bool holds_img = false;              // what the last encode wrote: images (tensor-core path) or k / vt (fp32 SIMT path)
     int max_pairs = 0;
     int pairs = 0;                       // pairs encoded by the last cotr_encode_context
 };
@@ -595,6 +598,8 @@ int ensure_encode_ws(cotr_model* m, int B) {
     Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh, &w.qk2, &w.vt2};
     for (Split16* b : bufs) ws_free(b);
     ws_free_f32(&w.ln_tmp);
+    if (w.kvimg) { cudaFree(w.kvimg); w.kvimg = nullptr; }
+    if (w.kvimg2) { cudaFree(w.kvimg2); w.kvimg2 = nullptr; }
     ws_free_f32(reinterpret_cast<float**>(&w.enc_st_a));
     ws_free_f32(reinterpret_cast<float**>(&w.enc_st_b));
     const size_t img = 2 * (size_t)B, tok = (size_t)B * kTokens;
@@ -606,6 +611,11 @@ int ensure_encode_ws(cotr_model* m, int B) {
         ws_alloc(&w.ffh, tok * kFF) || ws_alloc_f32(&w.ln_tmp, tok * kDModel) ||
         ws_alloc_f32(reinterpret_cast<float**>(&w.enc_st_a), tok * 32) || ws_alloc_f32(reinterpret_cast<float**>(&w.enc_st_b), tok * 32))
         return 1;
+    COTR_CHECK_CUDA(cudaMalloc((void**)&w.kvimg, (size_t)B * kHeads * kAttnHeadImgBytes));
+    COTR_CHECK_CUDA(cudaMalloc((void**)&w.kvimg2, (size_t)B * kHeads * kAttnHeadImgBytes));
+    // the 16 pad bytes of every value key group are copied by the bulk TMA: keep them defined
+    COTR_CHECK_CUDA(cudaMemset(w.kvimg, 0, (size_t)B * kHeads * kAttnHeadImgBytes));
+    COTR_CHECK_CUDA(cudaMemset(w.kvimg2, 0, (size_t)B * kHeads * kAttnHeadImgBytes));
     w.cap_pairs = B;
     return 0;
 }
@@ -706,12 +716,14 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
             // q|k and v^T alternate between two buffers: with tile-level dependencies the next layer's projection of a
             // row tile may run while other tiles of this layer still attend to the old keys / values
             const Split16 qk_l = (l & 1) ? w.qk2 : w.qk, vt_l = (l & 1) ? w.vt2 : w.vt;
+            unsigned char* const kvimg_l = (l & 1) ? w.kvimg2 : w.kvimg;
             {
                 GemmParams p = gemm_base(T, 3 * kDModel, kDModel, cs(xin), kDModel, e.qkv.w, e.qkv.wtc, e.qkv.wtc_scale, qk_l, 2 * kDModel);
                 p.addmat = e.add_qkv_tc; p.add_period = kTokens; p.ld_add = 3 * kDModel;
                 p.remap = 1;
                 p.blk_map[0] = 0; p.blk_map[1] = kDModel; p.blk_map[2] = -1;
                 p.vt = vt_l; p.n_vt = 1;
+                p.kv_img = kvimg_l; p.blk_map[1] = -1000;           // keys and values go straight into the attention operand images
                 if (ln_in) { p.a_ln_cs = e.qkv.cs; p.a_ln_part = w.enc_st_b; }
                 if (launch_tc(r, p, DEP_TILE)) return 1;
             }
@@ -719,6 +731,7 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
             a.q = cs(qk_l); a.ldq = 2 * kDModel;
             a.k = offset(cs(qk_l), kDModel); a.ldk = 2 * kDModel;
             a.vt = cs(vt_l); a.vt_pair_stride = kVtLayer;
+            a.kv_img = kvimg_l; a.img_pair_stride = kHeads * kAttnHeadImgBytes;
             a.out = w.ao; a.ldo = kDModel;
             a.nq = kTokens; a.npairs = B; a.pair0 = 0;
             if (run_attention(r, a, DEP_SPAN, kTokens / 128)) return 1;
@@ -744,15 +757,19 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
                 p.blk_map[2 * l + 1] = -(l + 1);
             }
             p.vt = ctx->vt; p.n_vt = kDecLayers;
+            p.kv_img = ctx->img;
+            for (int l = 0; l < kDecLayers; ++l) p.blk_map[2 * l] = -1000 - l;
             p.a_ln_cs = m->kv_all.cs; p.a_ln_part = w.enc_st_b;
             if (launch_tc(r, p, DEP_TILE)) return 1;
         }
         ctx->pairs = B;
+        ctx->holds_img = true;
         m->last_pairs = B;
         return 0;
     }
     // default schedule (and the fp32 SIMT cross-check path): explicit LayerNorm launches, the checkpoint's weights as they are
     m->last_mem_pre_ln = false;
+    const bool tc = m->gemm_path == 0;      // tensor-core path: keys / values are written as attention operand images
     const int n_enc_dbg = (g_tc_variant >> 20) & 7;
     for (int l = 0; l < (n_enc_dbg ? n_enc_dbg : kEncLayers); ++l) {
         const EncLayer& e = m->enc[l];
@@ -762,12 +779,14 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
             p.remap = 1;
             p.blk_map[0] = 0; p.blk_map[1] = kDModel; p.blk_map[2] = -1;
             p.vt = w.vt; p.n_vt = 1;
+            if (tc) { p.kv_img = w.kvimg; p.blk_map[1] = -1000; }
             if (run_gemm(r, p, nullptr)) return 1;
         }
         AttnParams a{};
         a.q = cs(w.qk); a.ldq = 2 * kDModel;
         a.k = offset(cs(w.qk), kDModel); a.ldk = 2 * kDModel;
         a.vt = cs(w.vt); a.vt_pair_stride = kVtLayer;
+        if (tc) { a.kv_img = w.kvimg; a.img_pair_stride = kHeads * kAttnHeadImgBytes; }
         a.out = w.ao; a.ldo = kDModel;
         a.nq = kTokens; a.npairs = B; a.pair0 = 0;
         if (run_attention(r, a)) return 1;
@@ -791,9 +810,14 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
             p.blk_map[2 * l + 1] = -(l + 1);
         }
         p.vt = ctx->vt; p.n_vt = kDecLayers;
+        if (tc) {
+            p.kv_img = ctx->img;
+            for (int l = 0; l < kDecLayers; ++l) p.blk_map[2 * l] = -1000 - l;
+        }
         if (run_gemm(r, p, nullptr)) return 1;
     }
     ctx->pairs = B;
+    ctx->holds_img = tc;
     m->last_pairs = B;
     return 0;
 }
@@ -839,6 +863,7 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
             a.q = q; a.ldq = ldq;
             a.k = offset(cs(ctx->k), (size_t)l * kDModel); a.ldk = kKCols;
             a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
+            if (ctx->holds_img) { a.kv_img = ctx->img + (size_t)l * kHeads * kAttnHeadImgBytes; a.img_pair_stride = (size_t)kDecLayers * kHeads * kAttnHeadImgBytes; }
             a.out = w.dao; a.ldo = kDModel;
             a.nq = nq; a.npairs = npairs; a.pair0 = pair0;
             if (run_attention(r, a, DEP_TILE)) return 1;
@@ -872,6 +897,7 @@ int decode_chunk(cotr_model* m, const cotr_context* ctx, const float* queries, f
             a.q = q; a.ldq = ldq;
             a.k = offset(cs(ctx->k), (size_t)l * kDModel); a.ldk = kKCols;
             a.vt = offset(cs(ctx->vt), (size_t)l * kVtLayer); a.vt_pair_stride = kDecLayers * kVtLayer;
+            if (ctx->holds_img) { a.kv_img = ctx->img + (size_t)l * kHeads * kAttnHeadImgBytes; a.img_pair_stride = (size_t)kDecLayers * kHeads * kAttnHeadImgBytes; }
             a.out = w.dao; a.ldo = kDModel;
             a.nq = nq; a.npairs = npairs; a.pair0 = pair0;
             if (run_attention(r, a)) return 1;
@@ -902,6 +928,8 @@ int decode_impl(cotr_model* m, const cotr_context* ctx, const float* queries, in
     COTR_CHECK(ctx && ctx->model == m, "cotr_decode: context does not belong to this model");
     COTR_CHECK(B >= 1 && B == ctx->pairs, "cotr_decode: B = %d but the context holds %d pairs", B, ctx ? ctx->pairs : -1);
     COTR_CHECK(Q >= 0, "cotr_decode: negative Q");
+    COTR_CHECK(ctx->holds_img == (m->gemm_path == 0), "cotr_decode: the context was encoded under the other matrix-multiply path "
+               "(cotr_set_gemm_path): re-encode it");
     if (Q == 0) return 0;
     COTR_CHECK_CUDA(cudaSetDevice(m->device));
     const long long total = (long long)B * Q;
@@ -1159,6 +1187,8 @@ void cotr_destroy(cotr_model* m) {
                        &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2, &w.t2, &w.qk2, &w.vt2};
     for (Split16* b : bufs) ws_free(b);
     if (w.sync_ctr) cudaFree(w.sync_ctr);
+    if (w.kvimg) cudaFree(w.kvimg);
+    if (w.kvimg2) cudaFree(w.kvimg2);
     float** fbufs[] = {&w.ln_tmp, &w.dln_tmp, &w.img_stage, &w.q_stage, &w.pred_stage,
                        reinterpret_cast<float**>(&w.enc_st_a), reinterpret_cast<float**>(&w.enc_st_b),
                        reinterpret_cast<float**>(&w.dec_st_a), reinterpret_cast<float**>(&w.dec_st_b)};
@@ -1178,7 +1208,9 @@ int cotr_context_create(cotr_model* m, int max_pairs, cotr_context** out) {
     cotr_context* c = new cotr_context();
     c->model = m;
     c->max_pairs = max_pairs;
-    if (ws_alloc(&c->k, (size_t)max_pairs * kTokens * kKCols) || ws_alloc(&c->vt, (size_t)max_pairs * kDecLayers * kVtLayer)) {
+    const size_t img_bytes = (size_t)max_pairs * kDecLayers * kHeads * kAttnHeadImgBytes;
+    if (ws_alloc(&c->k, (size_t)max_pairs * kTokens * kKCols) || ws_alloc(&c->vt, (size_t)max_pairs * kDecLayers * kVtLayer) ||
+        cudaMalloc((void**)&c->img, img_bytes) != cudaSuccess || cudaMemset(c->img, 0, img_bytes) != cudaSuccess) {
         set_error("cotr_context_create: out of device memory for %d pairs", max_pairs);
         cotr_context_destroy(c);
         return 1;
@@ -1191,6 +1223,7 @@ void cotr_context_destroy(cotr_context* c) {
     if (!c) return;
     ws_free(&c->k);
     ws_free(&c->vt);
+    if (c->img) cudaFree(c->img);
     delete c;
 }
 

@@ -62,6 +62,7 @@ __device__ __forceinline__ bool out_location(const GemmParams& p, int row, int n
     int col = nb;
     if (p.remap) {
         const int m = p.blk_map[nb >> 8];
+        if (m < 0 && p.kv_img != nullptr) { base = 0; return true; }      // attention operand image: store16 places it
         if (m < 0) {
             const int pair = row >> 9, key = row & (kTokens - 1);
             base = ((size_t)(pair * p.n_vt + (-m - 1)) * kDModel + (nb & 255)) * kTokens + key;
@@ -82,6 +83,38 @@ __device__ __forceinline__ void store16(const GemmParams& p, int row, int nb, co
         return;
     }
     size_t base;
+    if (p.remap && p.kv_img != nullptr && p.blk_map[nb >> 8] < 0) {
+        // attention operand images (common.cuh): row = pair * 512 + key, columns nb .. nb+15 = head dims d0 .. d0+15 of
+        // head (nb % 256) / 32.  Lanes hold consecutive keys.
+        const int m = p.blk_map[nb >> 8];
+        const bool is_key = m <= -1000;
+        const int slot = is_key ? -1000 - m : -m - 1;
+        const int pair = row >> 9, key = row & (kTokens - 1);
+        const int c = nb & 255, head = c >> 5, d0 = c & 31;
+        unsigned char* img = p.kv_img + ((size_t)(pair * p.n_vt + slot) * kHeads + head) * kAttnHeadImgBytes;
+        if (is_key) {              // two groups of 8 head dims: one 16-byte piece per plane each (512-byte runs per warp)
+            uint4 h0, l0, h1, l1;
+            split_f16x2(v[0], v[1], h0.x, l0.x);   split_f16x2(v[2], v[3], h0.y, l0.y);
+            split_f16x2(v[4], v[5], h0.z, l0.z);   split_f16x2(v[6], v[7], h0.w, l0.w);
+            split_f16x2(v[8], v[9], h1.x, l1.x);   split_f16x2(v[10], v[11], h1.y, l1.y);
+            split_f16x2(v[12], v[13], h1.z, l1.z); split_f16x2(v[14], v[15], h1.w, l1.w);
+            unsigned char* d = img + (size_t)(d0 >> 3) * (kTokens * 16) + (size_t)key * 16;
+            *reinterpret_cast<uint4*>(d) = h0;
+            *reinterpret_cast<uint4*>(d + kTokens * 16) = h1;
+            *reinterpret_cast<uint4*>(d + kAttnKPlaneBytes) = l0;
+            *reinterpret_cast<uint4*>(d + kAttnKPlaneBytes + kTokens * 16) = l1;
+        } else {                   // values: 8 consecutive keys of one head dim share a 16-byte piece
+            __half* d = reinterpret_cast<__half*>(img + kAttnKImgBytes + (size_t)(key >> 3) * kAttnVGroupBytes + (size_t)d0 * 16) + (key & 7);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                __half h, l;
+                split_f16(v[j], h, l);
+                d[j * 8] = h;                        // next head dim: + 16 bytes
+                d[j * 8 + 32 * 8] = l;               // lo rows follow the 32 hi rows of the key group
+            }
+        }
+        return;
+    }
     if (out_location(p, row, nb, base)) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {       // lanes hold consecutive keys -> each store is a coalesced 64-byte run
