@@ -63,6 +63,19 @@ def forced_cycle_consistency(engine, img_a, img_b, queries_a, max_corrs):
     return corr_f[idx_b][order][:max_corrs], err[order][:max_corrs]
 
 
+def compare_runs(single, sharded):
+    """Two runs of the same job whose model calls were batched differently (1 rank vs N ranks).  The network's answers
+    agree to ~1e-6 of the image, not bit for bit (the GEMM tile shapes follow the rows per launch), so the 2048 survivors
+    of the cycle-error ranking may differ near the cut: report the overlap and the differences on the common points."""
+    same_order = single.shape == sharded.shape and bool(np.array_equal(single[:, :2], sharded[:, :2]))
+    a = {tuple(r[:2]): r[2:] for r in single}
+    common = [(a[tuple(r[:2])], r[2:]) for r in sharded if tuple(r[:2]) in a]
+    diff = np.array([np.abs(x - y).max() for x, y in common]) if common else np.zeros(0)
+    return {"same_source_points": same_order, "common_source_points": len(common), "of": int(sharded.shape[0]),
+            "max_abs_diff_px": float(diff.max()) if diff.size else None,
+            "median_abs_diff_px": float(np.median(diff)) if diff.size else None}
+
+
 def run_config(config, rank, local_rank, world, steps=2, cpu_rate=None):
     """One JSON line on rank 0 (same keys as bench.py's headline line where they apply)."""
     import torch
@@ -136,9 +149,7 @@ def run_config(config, rank, local_rank, world, steps=2, cpu_rate=None):
             eng1 = FasterSparseEngine(native, 32, mode='tile', rescue_stranded=True)
             single = _quiet(lambda: forced_cycle_consistency(eng1, img_a, img_b, queries, n_corr))[0] if rank == 0 else None
             if rank == 0:
-                same_set = single.shape == corrs.shape and bool(np.array_equal(single[:, :2], corrs[:, :2]))
-                runs["vs_single_gpu"] = {"same_source_points": same_set,
-                                         "max_abs_diff_px": float(np.abs(single - corrs).max()) if same_set else None}
+                runs["vs_single_gpu"] = compare_runs(single, corrs)
             dist.barrier()
         value, n_points = runs["FasterSparseEngine+cycle"]["query_points_per_s"], int(corrs.shape[0])
         metric = "query-points/sec (FasterSparseEngine, 2048 cycle-consistent correspondences, 1024x1024 pair)"
