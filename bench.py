@@ -6,14 +6,17 @@
 Workload (BASELINE.json configs[1], the one `metric` is quoted on): per GPU one synthetic 256x256 image pair laid side
 by side (1,3,256,512) and 1024 random queries, no zoom; a "step" is one pass of the hot path over that batch
 (COTR.forward: backbone -> input_proj -> encoder -> decoder -> head).  Weak scaling: every rank processes its own pair
-(independent pairs shard with no data-path collective); for N > 1 the (N,1024,2) results are all-gathered over NCCL
-inside the timed step (the path's only exchange).
+(independent pairs shard with no data-path collective); for N > 1 every step hands its (1,1024,2) result to the result
+exchange on a side stream (the path's only exchange: this library's peer-memory push over NVLink, cotr_exchange; NCCL
+all-gather when the ranks cannot map each other's memory).
 
 One JSON line on rank 0:
   value      query-points/s, whole job, inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps
   e2e        same metric end to end from pinned HOST buffers: N = 1 through the C-ABI host-buffer call
-             (cotr_forward_host: H2D + forward + D2H inside); N > 1 through the Python API with the NCCL result gather
-             and the D2H read of the gathered (N,1024,2) block inside the timed region
+             (cotr_forward_host: H2D + forward + D2H inside); N > 1 through the Python API with the result exchange
+             (push, wait for all ranks) and the D2H read of the gathered (N,1024,2) block inside the timed region
+  result_exchange  (N > 1) transport used, the last step's gathered block checked against a plain NCCL all-gather, and
+             the per-rank step times with and without the exchange (what, if anything, the exchange costs the step)
   roofline   dominant kernel family of the step: its share of the kernel time comes from a per-launch CUDA-event pass
              (library profiler, eager), its time from share x the TIMED graph-replayed step - so kernel_ms_per_step
              can never exceed ms_per_step; `whole_step` = algorithmic FLOP / timed step
@@ -283,17 +286,22 @@ def run_native(args, rank, local_rank, world):
     img_pin = torch.from_numpy(img_np).pin_memory()
     q_pin = torch.from_numpy(q_np).pin_memory()
     out_pin = torch.empty((1, N_QUERIES, 2), dtype=torch.float32).pin_memory()
-    gathered = torch.empty((world, N_QUERIES, 2), dtype=torch.float32, device=dev) if world > 1 else None
     gathered_pin = torch.empty((world, N_QUERIES, 2), dtype=torch.float32).pin_memory() if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     from cotr_b200.inference.sharding import AsyncGather
-    gather = AsyncGather((1, N_QUERIES, 2), dev)          # N > 1: NCCL all-gather of the 8 KB blocks on a side stream
+    # N > 1: the 8 KB blocks are exchanged on a side stream - this library's peer-memory push over NVLink on one node, NCCL otherwise
+    gather = AsyncGather((1, N_QUERIES, 2), dev)
+    last = {}
 
     def step():
         pred = model(img, queries)["pred_corrs"]
         gather.submit(pred)
+        last["pred"] = pred
         return pred
+
+    def step_solo():                          # control: the same step without handing the result to the exchange
+        return model(img, queries)["pred_corrs"]
 
     def barrier():
         gather.wait()
@@ -312,6 +320,19 @@ def run_native(args, rank, local_rank, world):
     # ---- value: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps ----------
     dev_ms = _timed_steps(step, flush, args.steps, barrier)
     launches_per_step = nat.last_launch_count()
+    gather_ok, solo_ms, rank_ms = None, dev_ms, [dev_ms]
+    if world > 1:
+        got = gather.wait()                    # the last step's blocks of all ranks, checked against a plain collective
+        gather.check()
+        want = torch.empty_like(got)
+        dist.all_gather_into_tensor(want, last["pred"])
+        gather_ok = bool(torch.equal(got, want))
+        if not args.quick:
+            solo_ms = _timed_steps(step_solo, flush, args.steps, barrier)
+        per_rank = torch.zeros((world, 2), dtype=torch.float64, device=dev)
+        per_rank[rank, 0], per_rank[rank, 1] = dev_ms, solo_ms
+        dist.all_reduce(per_rank)
+        rank_ms = per_rank.tolist()
 
     # ---- e2e: host buffers in, host result out, every copy inside the timed region ----------------------------------
     img_h, q_h, out_h = img_pin.numpy(), q_pin.numpy(), out_pin.numpy()
@@ -321,12 +342,12 @@ def run_native(args, rank, local_rank, world):
         e2e_api = "cotr_forward_host (C ABI, pinned host buffers)"
         d2h = int(out_pin.numel() * 4)
     else:
-        def e2e_step():                      # the multi-GPU job as a user runs it: H2D, forward, NCCL gather, D2H of the gathered block
+        def e2e_step():                      # the multi-GPU job as a user runs it: H2D, forward, result exchange, D2H of the gathered block
             pred = model(img_pin.to(dev, non_blocking=True), q_pin.to(dev, non_blocking=True))["pred_corrs"]
-            dist.all_gather_into_tensor(gathered, pred)
-            gathered_pin.copy_(gathered, non_blocking=True)
+            gather.submit(pred)
+            gathered_pin.copy_(gather.wait(), non_blocking=True)
             torch.cuda.current_stream().synchronize()
-        e2e_api = "COTR.forward on pinned host tensors + nccl all_gather + D2H of the gathered (N,1024,2) block"
+        e2e_api = f"COTR.forward on pinned host tensors + result exchange ({gather.backend}) + D2H of the gathered (N,1024,2) block"
         d2h = int(gathered_pin.numel() * 4)
     for _ in range(3):
         e2e_step()
@@ -391,8 +412,11 @@ def run_native(args, rank, local_rank, world):
     # max over ranks
     t = torch.tensor([dev_ms, e2e_ms, c4_ms], dtype=torch.float64, device=dev)
     if world > 1:
+        gather.check(); gather4.check()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, c4_ms = t.tolist()
+    backends = (gather.backend, gather4.backend)
+    gather.close(); gather4.close()          # collective: buffers are unmapped only after every rank has stopped pushing
     if rank != 0:
         return
 
@@ -438,9 +462,15 @@ def run_native(args, rank, local_rank, world):
                     "ms_per_step": c4_ms, "steps": c4_steps, "launches_per_step": c4_launches,
                     "roofline": {"bound": "tensor", "algorithmic_gflop": c4_flop / 1e9, "achieved": c4_tf, "peak": peaks["bf16_tflops"],
                                  "unit": "TFLOP/s", "frac": c4_tf / peaks["bf16_tflops"]},
-                    "result_gather": "nccl all_gather on a side stream (AsyncGather)" if world > 1 else "none (single GPU)"},
+                    "result_gather": f"AsyncGather on a side stream, transport: {backends[1]}" if world > 1 else "none (single GPU)"},
         "clocks": clocks,
     }
+    if world > 1:
+        line["result_exchange"] = {
+            "transport": backends[0], "last_step_equals_nccl_all_gather": gather_ok,
+            "ms_per_step_by_rank": [r[0] for r in rank_ms], "ms_per_step_by_rank_without_exchange": [r[1] for r in rank_ms],
+            "note": "peer = cotr_exchange: this library's push kernel stores each rank's block into every peer's buffer over NVLink on a side "
+                    "stream; the second list is a control run of the same steps that never hands its result over"}
     if args.quick:
         line.pop("config4")
         line["roofline"] = None

@@ -50,6 +50,14 @@ _PROTOTYPES = {
     "cotr_group_tasks": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "cotr_rasterize_triangles": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_exchange_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "cotr_exchange_handle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_exchange_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "cotr_exchange_connect_local": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "cotr_exchange_push": (ctypes.c_longlong, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "cotr_exchange_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]),
+    "cotr_exchange_status": (ctypes.c_int, [ctypes.c_void_p]),
+    "cotr_exchange_destroy": (None, [ctypes.c_void_p]),
     "cotr_set_graph_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cotr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "cotr_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -240,6 +248,73 @@ class NativeModel:
         if self.handle is not None:
             lib().cotr_destroy(self.handle)
             self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+EXCHANGE_HANDLE_BYTES = 64
+
+
+class NativeExchange:
+    """One rank's end of the peer-memory result exchange (cotr_exchange, include/cotr_b200.h): `push` writes this rank's
+    block into every peer's buffer over NVLink, `wait` gathers one step's blocks in rank order.  Connecting is the
+    caller's job: `handle()` -> all-gather the 64-byte handles between the processes -> `connect(handles)`; exchanges
+    living in one process use `connect_local(all_exchanges)`."""
+
+    def __init__(self, device_index, rank, world, block_bytes, slots=4):
+        self.device_index, self.rank, self.world, self.block_bytes, self.slots = int(device_index), int(rank), int(world), int(block_bytes), int(slots)
+        h = ctypes.c_void_p()
+        check(lib().cotr_exchange_create(self.device_index, self.rank, self.world, self.block_bytes, self.slots, ctypes.byref(h)), "cotr_exchange_create")
+        self.handle_ = h
+
+    def handle(self):
+        buf = ctypes.create_string_buffer(EXCHANGE_HANDLE_BYTES)
+        check(lib().cotr_exchange_handle(self.handle_, buf), "cotr_exchange_handle")
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: the `handle()` of every rank, in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == self.world * EXCHANGE_HANDLE_BYTES
+        check(lib().cotr_exchange_connect(self.handle_, ctypes.create_string_buffer(blob, len(blob))), "cotr_exchange_connect")
+
+    def connect_local(self, exchanges):
+        arr = (ctypes.c_void_p * self.world)(*[e.handle_ for e in exchanges])
+        check(lib().cotr_exchange_connect_local(self.handle_, arr), "cotr_exchange_connect_local")
+
+    def _stream(self, stream):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device_index)
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def push(self, block, stream=None):
+        """block: contiguous CUDA tensor of this rank (at most block_bytes, a multiple of 16 bytes).  Returns the step number."""
+        assert block.is_cuda and block.is_contiguous() and block.device.index == self.device_index
+        seq = lib().cotr_exchange_push(self.handle_, _ptr(block), block.numel() * block.element_size(), self._stream(stream))
+        if seq < 0:
+            raise RuntimeError(f"cotr_exchange_push failed: {last_error()}")
+        return int(seq)
+
+    def wait(self, seq, out=None, bytes_per_rank=None, stream=None):
+        """Enqueue the wait for step `seq`; `out` (contiguous CUDA tensor, or None) receives the blocks in rank order."""
+        sizes = None
+        if bytes_per_rank is not None:
+            sizes = (ctypes.c_size_t * self.world)(*[int(b) for b in bytes_per_rank])
+        need = sum(int(b) for b in bytes_per_rank) if bytes_per_rank is not None else self.world * self.block_bytes
+        if out is not None:
+            assert out.is_cuda and out.is_contiguous() and out.numel() * out.element_size() >= need
+        check(lib().cotr_exchange_wait(self.handle_, int(seq), _ptr(out) if out is not None else None, sizes, self._stream(stream)), "cotr_exchange_wait")
+
+    def status(self):
+        return int(lib().cotr_exchange_status(self.handle_))
+
+    def close(self):
+        if self.handle_:
+            lib().cotr_exchange_destroy(self.handle_)
+            self.handle_ = None
 
     def __del__(self):
         try:

@@ -2,7 +2,8 @@
 
 One process per GPU (torchrun).  Pairs (and the zoom-in engines' contexts) are independent, so the only exchange is
 the gather of the (B,Q,2) fp32 predictions - 8 KB per 1024 queries.  Works with the `nccl` backend on CUDA tensors and
-with `gloo` on CPU tensors (used by the CPU tests).
+with `gloo` on CPU tensors (used by the CPU tests); the pipelined gather of `AsyncGather` uses this library's own
+peer-memory exchange over NVLink when the ranks share a node.
 
 Two entry points:
   * `forward_sharded(model, img, queries)`: BASELINE.json configs[3] - one batch of independent pairs, each rank runs
@@ -68,41 +69,117 @@ def forward_sharded(model, img, queries, group=None):
     return gather_predictions(local, img.shape[0], group)
 
 
+def open_exchange(block_bytes, device, group=None, slots=4):
+    """This rank's end of a peer-memory result exchange (`cotr_exchange`, csrc/peer_exchange.cu) connected to all ranks
+    of `group`, or None when the ranks cannot map each other's device memory (different nodes, no peer access, block size
+    not a multiple of 16 bytes).  Collective: every rank calls it, and all ranks get the same kind of answer."""
+    import socket
+    from cotr_b200 import capi
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ex, handle, ok = None, b"\0" * capi.EXCHANGE_HANDLE_BYTES, int(block_bytes % 16 == 0 and device.type == "cuda")
+    if ok:
+        try:
+            ex = capi.NativeExchange(device.index if device.index is not None else torch.cuda.current_device(), rank, world, block_bytes, slots)
+            handle = ex.handle()
+        except (RuntimeError, OSError, AttributeError):
+            ok = 0
+    infos = [None] * world
+    dist.all_gather_object(infos, (socket.gethostname(), handle, ok), group=group)
+    if ok and len({host for host, _, _ in infos}) == 1 and all(o for _, _, o in infos):
+        try:
+            ex.connect([h for _, h, _ in infos])
+        except RuntimeError:
+            ok = 0
+    else:
+        ok = 0
+    agreed = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=group)        # also: nobody pushes before everybody has mapped
+    if int(agreed.item()) == 0:
+        if ex is not None:
+            ex.close()
+        return None
+    return ex
+
+
 class AsyncGather:
     """The result gather of a stream of independent steps, kept off the compute stream's critical path.
 
-    `submit(pred)` enqueues the all-gather of this rank's (b,Q,2) block on a side stream that waits (CUDA event) for the
-    kernels that produce `pred`; the compute stream continues with the next step at once.  Blocks are gathered into
-    one of two alternating buffers (the step after next reuses the first), `wait()` joins the side stream into the
-    current stream and returns the most recent gathered tensor.  NCCL calls are issued in the same order on every
-    rank, which is all NCCL needs; the 8 KB exchange is pure latency, so overlapping it with the next forward hides it."""
+    `submit(pred)` hands this rank's (b,Q,2) block to a side stream that waits (CUDA event) for the kernels that produce
+    `pred`; the compute stream continues with the next step at once.  `wait()` joins the side stream into the current
+    stream and returns the most recent gathered tensor.  Two transports:
+      * "peer" (default on one node): `cotr_exchange` - the side stream runs this library's push kernel, which stores the
+        block into every peer's symmetric buffer over NVLink and never waits for anybody; only `wait()` polls for the
+        other ranks' blocks of that step.  Steps that are never waited for are simply overwritten `slots` steps later;
+      * "nccl": `all_gather_into_tensor` on the side stream into alternating buffers (every rank's collective kernel
+        waits for every other rank, step by step) - the fallback across nodes.
+    Calls are issued in the same order on every rank."""
 
-    def __init__(self, block_shape, device, group=None):
+    def __init__(self, block_shape, device, group=None, backend="auto", slots=4):
+        assert backend in ("auto", "peer", "nccl")
         self.group = group
         self.world = dist.get_world_size(group) if _active(group) else 1
         self.side = torch.cuda.Stream(device=device) if self.world > 1 else None
+        self.block_shape = tuple(block_shape)
         self.bufs = [torch.empty((self.world * block_shape[0],) + tuple(block_shape[1:]), dtype=torch.float32, device=device) for _ in range(2)]
         self.turn = 0
         self.last = None
+        self.seq = 0
+        self.exchange = None
+        if self.world > 1 and backend != "nccl":
+            block_bytes = 4 * int(np.prod(block_shape))
+            self.exchange = open_exchange(block_bytes, torch.device(device), group, slots)
+            if self.exchange is None and backend == "peer":
+                raise RuntimeError("AsyncGather(backend='peer'): the ranks cannot map each other's device memory")
+        self.backend = "local" if self.world == 1 else ("peer" if self.exchange is not None else "nccl")
 
     def submit(self, pred):
         if self.world == 1:
             self.last = pred
             return
-        out = self.bufs[self.turn]
-        self.turn ^= 1
+        pred = pred.contiguous()
         ready = torch.cuda.Event()
         ready.record()                                   # after the kernels of this step on the compute stream
         pred.record_stream(self.side)
+        if self.exchange is not None:
+            assert tuple(pred.shape) == self.block_shape and pred.dtype == torch.float32
+            self.side.wait_event(ready)
+            self.seq = self.exchange.push(pred, stream=self.side)
+            self.last = None
+            return
+        out = self.bufs[self.turn]
+        self.turn ^= 1
         with torch.cuda.stream(self.side):
             self.side.wait_event(ready)
             dist.all_gather_into_tensor(out, pred, group=self.group)
         self.last = out
 
     def wait(self):
+        if self.exchange is not None and self.last is None and self.seq > 0:
+            out = self.bufs[self.turn]
+            self.turn ^= 1
+            self.exchange.wait(self.seq, out=out, stream=self.side)
+            self.last = out
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
         return self.last
+
+    def check(self):
+        """Host-synchronising health check of the peer transport (0 = fine); raises on a missed or overwritten step."""
+        if self.exchange is None:
+            return 0
+        self.side.synchronize()
+        status = self.exchange.status()
+        if status != 0:
+            raise RuntimeError("peer result exchange: " + ("a rank never published the step" if status == 1 else "a waited step was overwritten"))
+        return 0
+
+    def close(self):
+        """Collective: no rank may free its buffer while another one can still push into it."""
+        if self.exchange is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self.exchange.close()
+            self.exchange = None
 
 
 class LazyCanvases:

@@ -125,6 +125,39 @@ int cotr_group_tasks(int device, const double* pts_dev, const double* box_dev, i
  * (x + 0.5, y + 0.5) covered by a triangle (top-left fill rule), zero elsewhere.  `device` is the CUDA device index. */
 int cotr_rasterize_triangles(int device, const float* tris_dev, int n_tri, int H, int W, float* out_dev, void* cuda_stream);
 
+/* ---- result exchange between the GPUs of one node over NVLink peer memory -------------------------------------------
+ * The reference has no multi-GPU inference; its closest call site is the loop over independent pairs of
+ * demo_reconstruction.py:44-49, which BASELINE.json configs[3] / configs[4] spread over 8 GPUs.  Pairs shard, weights are
+ * replicated, and the only exchange is the all-gather of every rank's block of predictions.  cotr_exchange does that
+ * gather with this library's own kernels instead of a collective: a push writes the block straight into every peer's
+ * symmetric buffer (nobody waits in order to send), a wait polls the local arrival flags of one step and copies the
+ * gathered blocks out.  One process per GPU:
+ *     cotr_exchange_create(dev, rank, world, block_bytes, slots, &ex);  cotr_exchange_handle(ex, my_handle);
+ *     <all-gather the 64-byte handles with whatever the host program has: torch.distributed, MPI, a file>
+ *     cotr_exchange_connect(ex, all_handles);
+ *     seq = cotr_exchange_push(ex, pred_dev, bytes, stream);  ...  cotr_exchange_wait(ex, seq, gathered_dev, NULL, stream);
+ * Every rank must push the same sequence of steps.  `slots` (2..64) steps are kept; a wait for a step that a faster
+ * peer has meanwhile overwritten is detected (cotr_exchange_status == 2), a peer that never publishes the step within
+ * ~3 s gives status 1 instead of a hang.  A rank that alternates push and wait can never be overwritten.  Sizes and device
+ * addresses are multiples of 16 bytes.  One stream at a time per exchange. */
+typedef struct cotr_exchange cotr_exchange;
+#define COTR_EXCHANGE_HANDLE_BYTES 64
+int cotr_exchange_create(int device, int rank, int world, size_t block_bytes, int slots, cotr_exchange** out);
+/* handle_out: COTR_EXCHANGE_HANDLE_BYTES bytes (a cudaIpcMemHandle_t of this rank's buffer) */
+int cotr_exchange_handle(cotr_exchange* ex, void* handle_out);
+/* handles: world x COTR_EXCHANGE_HANDLE_BYTES bytes in rank order (the own entry is ignored) */
+int cotr_exchange_connect(cotr_exchange* ex, const void* handles);
+/* the same for exchanges that live in ONE process (one thread per GPU, or tests): all[r] = the exchange of rank r */
+int cotr_exchange_connect_local(cotr_exchange* ex, cotr_exchange* const* all);
+/* returns the step number (1, 2, ...) or -1 */
+long long cotr_exchange_push(cotr_exchange* ex, const void* block_dev, size_t bytes, void* cuda_stream);
+/* gathered_dev: the blocks of step `seq` concatenated in rank order (NULL: only wait); bytes_per_rank: world entries
+ * (HOST), NULL = every rank pushed block_bytes */
+int cotr_exchange_wait(cotr_exchange* ex, long long seq, void* gathered_dev, const size_t* bytes_per_rank, void* cuda_stream);
+/* 0 ok, 1 a peer never arrived, 2 a waited step was overwritten; meaningful after the stream of the wait synchronised */
+int cotr_exchange_status(const cotr_exchange* ex);
+void cotr_exchange_destroy(cotr_exchange* ex);
+
 /* cotr_forward / cotr_forward_host replay a CUDA graph per (B,Q) shape (captured on the second call with that shape;
  * inputs / outputs pass through internal staging buffers so the graph's addresses stay fixed).  0 disables it. */
 int cotr_set_graph_mode(cotr_model* m, int enabled);
