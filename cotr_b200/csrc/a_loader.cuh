@@ -44,8 +44,8 @@ __device__ __forceinline__ ARow decode_a_row(const GemmParams& p, int m) {
         r.iw0 = ow * p.stride - p.pad;
         if (p.a_mode == A_CONV_NHWC) {
             r.off = (size_t)n * p.H * p.W * p.C;
-        } else {  // A_STEM_NCHW: image n = 2*pair + half lives in columns [half*256, half*256+256) of the fp32 canvas
-            r.off = (size_t)(n >> 1) * 3 * 256 * 512 + (n & 1) * 256;
+        } else {  // A_STEM_NHWC4: pixel (2 oh, 2 ow) of the bordered canvas of image n = tap (0,0) of this output pixel
+            r.off = (size_t)n * kStemCanvasElems + ((size_t)(2 * oh) * kStemCanvasPitch + 2 * ow) * 4;
         }
     }
     return r;
@@ -65,29 +65,12 @@ __device__ __forceinline__ bool a_offset8(const GemmParams& p, const ARow& r, in
         off = r.off + ((size_t)ih * p.W + iw) * p.C + c;
         return true;
     }
+    if (p.a_mode == A_STEM_NHWC4) {      // k = kh * 32 + (pixel slot * 4 + channel): 32 contiguous halves per filter row
+        off = r.off + (size_t)(k >> 5) * (kStemCanvasPitch * 4) + (k & 31);
+        return true;
+    }
     off = r.off + k;
     return true;
-}
-
-// fp32 stem: elements k..k+3 (k % 4 == 0) of the 7x7x3 patch; zero outside the half image / beyond K.
-__device__ __forceinline__ float4 load_stem4(const GemmParams& p, const ARow& r, int k) {
-    float e[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r.valid) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int kk = k + t;
-            if (kk < p.K) {
-                const int tap = kk / 3;
-                const int c = kk - tap * 3;
-                const int kh = tap / 7;
-                const int kw = tap - kh * 7;
-                const int ih = r.ih0 + kh, iw = r.iw0 + kw;
-                if (ih >= 0 && ih < 256 && iw >= 0 && iw < 256)
-                    e[t] = __ldg(p.a_f32 + r.off + (size_t)c * 256 * 512 + (size_t)ih * 512 + iw);
-            }
-        }
-    }
-    return make_float4(e[0], e[1], e[2], e[3]);
 }
 
 }  // namespace cotr

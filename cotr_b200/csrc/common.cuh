@@ -211,20 +211,30 @@ inline CSplit16 cs(const Split16& s) { return CSplit16{s.hi, s.lo}; }
 inline Split16 offset(const Split16& s, size_t elems) { return Split16{s.hi + elems, s.lo + elems}; }
 inline CSplit16 offset(const CSplit16& s, size_t elems) { return CSplit16{s.hi + elems, s.lo + elems}; }
 
+// The stem's input.  The network input is an fp32 (B,3,256,512) NCHW canvas, two 256x256 images side by side.  The 7x7
+// stride-2 convolution reads it through a split16 copy made by one small kernel per forward (launch_stem_canvas): image
+// n = 2*pair + half as [kStemCanvasRows][kStemCanvasPitch] pixels of 4 halves (r, g, b, 0), the image at rows / columns
+// 3.., everything else zero (the convolution's padding, written once when the buffer is allocated).  A filter row of
+// output pixel (oh, ow) is then 8 consecutive pixels = 64 contiguous, 16-byte aligned bytes per plane starting at pixel
+// (2 oh + kh, 2 ow): no bounds checks, plain 16-byte cp.async like every other operand.  K = 7 rows x 8 pixel slots x 4
+// channels = 224, the weights carry zeros for slot 7 and channel 3.
+constexpr int kStemCanvasRows = 262, kStemCanvasPitch = 264;
+constexpr size_t kStemCanvasElems = (size_t)kStemCanvasRows * kStemCanvasPitch * 4;      // halves per image and plane
+constexpr int kStemK = 7 * 32;
+
 // How a GEMM finds row m, column k of its A operand.
 enum AMode : int {
     A_ROWMAJOR = 0,   // A[m * lda + k]
     A_CONV_NHWC = 1,  // implicit im2col over an NHWC activation: m -> (n, oh, ow), k -> (kh, kw, c)
-    A_STEM_NCHW = 2,  // implicit im2col over the fp32 (B,3,256,512) NCHW canvas, halves as separate images
+    A_STEM_NHWC4 = 2, // 7x7 stride-2 stem: implicit im2col over the zero-bordered split16 NHWC4 copy of the canvas (below)
     A_TOKENS = 3,     // m = pair*512 + i*32 + j gathers row ((2*pair + (j>>4))*16 + i)*16 + (j&15)
 };
 
 // D[M,N] = epilogue( A[M,K] * W[N,K]^T ).
 struct GemmParams {
     int M, N, K;
-    // A operand: split16 activation, or the fp32 input canvas for A_STEM_NCHW
+    // A operand: split16 activation (A_STEM_NHWC4: the stem canvas)
     CSplit16 a;
-    const float* a_f32;
     int a_mode;
     int lda;
     int H, W, C;      // convolution geometry: input height / width / channels (per image)
@@ -308,6 +318,8 @@ int launch_ln_partials(CSplit16 x, float2* part, int rows, cudaStream_t s);
 int launch_layernorm_twice(CSplit16 x, const float* g1, const float* b1, const float* g2, const float* b2, Split16 out, int rows, cudaStream_t s,
                            LaunchSync sync = LaunchSync{});
 int launch_query_encode(const float* queries, Split16 qpos, int rows, cudaStream_t s, LaunchSync sync = LaunchSync{});
+// fp32 (B,3,256,512) canvas -> the stem's bordered split16 NHWC4 operand (2B images of kStemCanvasElems halves per plane)
+int launch_stem_canvas(const float* img, Split16 canvas, int n_img, cudaStream_t s, LaunchSync sync = LaunchSync{});
 int launch_f32_to_split16(const float* in, Split16 out, size_t n, cudaStream_t s);
 int launch_split16_to_f32(CSplit16 in, float* out, size_t n, cudaStream_t s);
 

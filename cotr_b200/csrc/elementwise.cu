@@ -54,6 +54,25 @@ __global__ void maxpool_3x3s2_nhwc_kernel(const CSplit16 in, const Split16 out, 
     small_kernel_signal(sync, 0);
 }
 
+// The stem's operand (common.cuh "The stem's input"): fp32 (B,3,256,512) NCHW canvas -> per image n = 2*pair + half the
+// split16 NHWC4 copy with a zero border.  One thread per pixel: three coalesced channel reads, one 8-byte store per plane.
+__global__ void __launch_bounds__(256) stem_canvas_kernel(const float* __restrict__ img, const Split16 canvas, int n_img, const LaunchSync sync) {
+    small_kernel_wait(sync, 0);
+    const size_t total = (size_t)n_img * 256 * 256;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx & 255), y = (int)((idx >> 8) & 255), n = (int)(idx >> 16);
+        const float* src = img + (size_t)(n >> 1) * 3 * 256 * 512 + (size_t)y * 512 + (n & 1) * 256 + x;
+        const float r = __ldcg(src), g = __ldcg(src + 256 * 512), b = __ldcg(src + 2 * 256 * 512);
+        uint2 h, l;
+        split_f16x2(r, g, h.x, l.x);
+        split_f16x2(b, 0.f, h.y, l.y);
+        const size_t off = (size_t)n * kStemCanvasElems + ((size_t)(y + 3) * kStemCanvasPitch + (x + 3)) * 4;
+        *reinterpret_cast<uint2*>(canvas.hi + off) = h;
+        *reinterpret_cast<uint2*>(canvas.lo + off) = l;
+    }
+    small_kernel_signal(sync, 0);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -235,6 +254,12 @@ int launch_layernorm_f32(const float* x, const float* gamma, const float* beta, 
 int launch_query_encode(const float* queries, Split16 qpos, int rows, cudaStream_t s, LaunchSync sync) {
     if (rows <= 0) return 0;
     COTR_CHECK_CUDA(launch_kernel(query_encode_kernel, dim3(rows), dim3(128), 0, s, queries, qpos, rows, sync));
+    return 0;
+}
+
+int launch_stem_canvas(const float* img, Split16 canvas, int n_img, cudaStream_t s, LaunchSync sync) {
+    if (n_img <= 0) return 0;
+    COTR_CHECK_CUDA(launch_kernel(stem_canvas_kernel, dim3(grid_for((size_t)n_img * 256 * 256, 256)), dim3(256), 0, s, img, canvas, n_img, sync));
     return 0;
 }
 

@@ -11,7 +11,6 @@ constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
 
 // A[m, k..k+3] as fp32 (k % 4 == 0)
 __device__ __forceinline__ float4 load_a4_f32(const GemmParams& p, const ARow& r, int k) {
-    if (p.a_mode == A_STEM_NCHW) return load_stem4(p, r, k);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     size_t off;
     if (!a_offset8(p, r, k & ~7, off)) return v;     // all split16 operands have K % 8 == 0
@@ -114,7 +113,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p, floa
 // add-matrices and as the LayerNorm staging buffer of the SIMT path).
 int launch_gemm_simt_raw(const GemmParams& p, float* raw_out, cudaStream_t s) {
     COTR_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "gemm_simt: empty problem %d x %d x %d", p.M, p.N, p.K);
-    COTR_CHECK(p.a_mode == A_STEM_NCHW || (p.K & 7) == 0, "gemm_simt: split16 operands need K %% 8 == 0 (K=%d)", p.K);
+    COTR_CHECK((p.K & 7) == 0, "gemm_simt: split16 operands need K %% 8 == 0 (K=%d)", p.K);
     COTR_CHECK(p.a_mode != A_CONV_NHWC || (p.C & 7) == 0, "gemm_simt: NHWC conv needs C %% 8 == 0 (C=%d)", p.C);
     COTR_CHECK(p.ln_gamma == nullptr, "gemm_simt: fused LayerNorm is a tensor-core-path feature");
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);

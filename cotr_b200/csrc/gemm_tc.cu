@@ -17,8 +17,9 @@
 //   * activations: already split16 in HBM (the producer's epilogue split them), so warps 0-3 stage the A tile with
 //     asynchronous 16-byte copies (cp.async -> LDGSTS, zero-filled for im2col padding / row tails; 8 lanes cover one
 //     128-byte row on both sides: coalesced reads, conflict-free writes) whose completion arrives on the stage's
-//     mbarrier (cp.async.mbarrier.arrive.noinc) - no registers, no conversion, up to kStages chunks in flight.  Only
-//     the 7x7 stem reads the caller's fp32 canvas and converts in registers;
+//     mbarrier (cp.async.mbarrier.arrive.noinc) - no registers, no conversion, up to kStages chunks in flight.  The
+//     7x7 stem reads a zero-bordered split16 NHWC4 copy of the canvas (common.cuh) with the same 16-byte copies; the
+//     weight TMA of a stage completes on the SAME mbarrier (128 loader arrivals + 1 expect_tx), one wait per stage;
 //   * warp 4 (one lane) issues the TMA copies, warp 5 (one lane) issues tcgen05.mma and owns TMEM;
 //   * long reductions on under-filled grids are split over a thread-block cluster (1 x 1 x {2,4}) and reduce-scattered
 //     over TMEM lane quarters through distributed shared memory (st.async + mbarrier, no cluster barrier);
@@ -53,7 +54,7 @@ constexpr int BK = 64;
 constexpr int kThreads = 256;
 constexpr uint32_t kAPlane = BM * 128;         // one fp16 plane (hi or lo) of the 128 x 64 A tile: 128 rows x 128 bytes
 
-enum LoaderMode : int { LD_GATHER = 0, LD_CONV = 1, LD_STEM = 2 };
+enum LoaderMode : int { LD_GATHER = 0, LD_CONV = 1, LD_STEM4 = 2 };
 
 __host__ __device__ inline int tc_npad(int N) { return N >= 64 ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16; }
 
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
             mbar_wait(&empty[s], ph ^ 1u);
             if (threadIdx.x == 0 && it < 8) COTR_TS(3 + 2 * it);
             const int k0 = (it0 + it) * BK;
-            if constexpr (MODE != LD_STEM) {
+            {
                 const uint32_t dst = dst0 + (uint32_t)s * C::kStage;
                 int kh = 0, kw = 0, koff = k0 + kg * 8;          // LD_GATHER: koff = column inside the row
                 if constexpr (MODE == LD_CONV) {                 // C % 64 == 0: the chunk lies inside one filter tap
@@ -218,6 +219,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     koff = k0 - tap * p.C + kg * 8;
                     kh = tap / p.KW;
                     kw = tap - kh * p.KW;
+                }
+                if constexpr (MODE == LD_STEM4) {               // filter row kh = 64 contiguous bytes of the bordered canvas
+                    const int kk = k0 + kg * 8;
+                    koff = (kk >> 5) * (kStemCanvasPitch * 4) + (kk & 31);
                 }
                 const bool k_ok = (k0 + kg * 8) < p.K;
 #pragma unroll
@@ -235,48 +240,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmParams p
                     cp_async16(dst + kAPlane + i * 2048, p.a.lo + off, bytes);
                 }
                 cp_async_mbar_arrive_noinc(&full_a[s]);
-            } else {
-                uint8_t* a_hi = stage_base + (size_t)s * C::kStage + a_off;
-                uint8_t* a_lo = a_hi + kAPlane;
-                // the 8 patch elements this thread fetches are the same for its 8 rows: decode them once per chunk
-                int rel[8], dh[8], dw[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int kk = k0 + kg * 8 + t;
-                    const int tap = kk / 3, c = kk - tap * 3;
-                    const int kh = tap / 7, kw = tap - kh * 7;
-                    dh[t] = kk < p.K ? kh : -100000;             // beyond K: never in bounds -> zero
-                    dw[t] = kw;
-                    rel[t] = c * 256 * 512 + kh * 512 + kw;
-                }
-                // 4 rows x 8 scalar gathers in flight per pass (the loads are L2 hits of ~700 cycles: issue, then convert)
-#pragma unroll
-                for (int i0 = 0; i0 < 8; i0 += 4) {
-                    float e[4][8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const ARow& r = rows[i0 + i];
-                        const float* base = p.a_f32 + r.off + (ptrdiff_t)r.ih0 * 512 + r.iw0;
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const int ih = r.ih0 + dh[t], iw = r.iw0 + dw[t];
-                            const bool ok = r.valid && ih >= 0 && ih < 256 && iw >= 0 && iw < 256;
-                            e[i][t] = ok ? __ldg(base + rel[t]) : 0.f;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 hi, lo;
-                        split_f16x2(e[i][0], e[i][1], hi.x, lo.x);
-                        split_f16x2(e[i][2], e[i][3], hi.y, lo.y);
-                        split_f16x2(e[i][4], e[i][5], hi.z, lo.z);
-                        split_f16x2(e[i][6], e[i][7], hi.w, lo.w);
-                        *reinterpret_cast<uint4*>(a_hi + (i0 + i) * 2048) = hi;
-                        *reinterpret_cast<uint4*>(a_lo + (i0 + i) * 2048) = lo;
-                    }
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(&full_a[s]);
             }
             if (threadIdx.x == 0 && it < 8) COTR_TS(4 + 2 * it);
         }
@@ -776,7 +739,7 @@ int launch_one(const GemmParams& p, cudaStream_t s) {
     // Split-K over a thread-block cluster for long reductions on under-filled grids (the K loop is the serial part of
     // these latency-bound launches): 4 or 2 CTAs per output tile, each >= 4 chunks, at most ~one wave of CTAs.
     int ksplit = 1;
-    if constexpr (!LN && BN <= 64 && MODE != LD_STEM) {
+    if constexpr (!LN && BN <= 64 && MODE != LD_STEM4) {
         const int kc = (p.K + BK - 1) / BK;
         const long long ctas = (long long)grid.x * grid.y;
         if (!(g_tc_variant & 512) && kc >= (16 >> ((g_tc_variant >> 14) & 3))) {     // bring-up knob: bits 14-15
@@ -811,7 +774,7 @@ int launch_mode(const GemmParams& p, cudaStream_t s) {
         if (p.a_mode == A_CONV_NHWC && (p.C & 63) == 0) return launch_one<BN, LN, LD_CONV>(p, s);
     }
     if constexpr (!LN && BN == 64) {
-        if (p.a_mode == A_STEM_NCHW) return launch_one<64, false, LD_STEM>(p, s);
+        if (p.a_mode == A_STEM_NHWC4 && p.K == kStemK) return launch_one<64, false, LD_STEM4>(p, s);
     }
     set_error("gemm_tc: no kernel instantiation for a_mode %d, K %d, lda %d, C %d with tile N %d", p.a_mode, p.K, p.lda, p.C, BN);
     return 1;
@@ -920,7 +883,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s, GemmLaunchInfo* info) {
     static const long long kThrWide[4] = {96, 48, 1 << 30, 148};
     const long long thr64 = kThr[(g_tc_variant >> 10) & 3], thr128 = kThrWide[(g_tc_variant >> 12) & 3];
     if ((p.N % 128) == 0 && mt * (p.N / 128) >= thr128) return launch_mode<128, false>(p, s);
-    if (mt * ((p.N + 63) / 64) >= thr64 || p.a_mode == A_STEM_NCHW || (p.N % 32) != 0) return launch_mode<64, false>(p, s);
+    if (mt * ((p.N + 63) / 64) >= thr64 || p.a_mode == A_STEM_NHWC4 || (p.N % 32) != 0) return launch_mode<64, false>(p, s);
     return launch_mode<32, false>(p, s);
 }
 

@@ -38,6 +38,7 @@ struct DevConv {
     float wtc_scale = 1.f; // accumulator scale that undoes the image's power-of-two pre-scaling
     float* b = nullptr;    // FrozenBN shift
     int cout = 0, cin = 0, kh = 1, kw = 1, stride = 1, pad = 0;
+    bool stem = false;     // 7x7/2 stem over the bordered NHWC4 canvas: kw = 8 pixel slots, cin = 4 (common.cuh)
 };
 
 struct DevLinear {
@@ -80,7 +81,7 @@ struct Workspace {
     int cap_pairs = 0;
     int cap_rows = 0;
     // backbone (per image sizes x 2*cap_pairs), all split16
-    Split16 stem = kNoSplit, bx = kNoSplit, by = kNoSplit, bt1 = kNoSplit, bt2 = kNoSplit, bds = kNoSplit;
+    Split16 canvas = kNoSplit, stem = kNoSplit, bx = kNoSplit, by = kNoSplit, bt1 = kNoSplit, bt2 = kNoSplit, bds = kNoSplit;
     // encoder
     Split16 src = kNoSplit, xa = kNoSplit, xb = kNoSplit, qk = kNoSplit, vt = kNoSplit, ao = kNoSplit, ffh = kNoSplit;
     Split16 qk2 = kNoSplit, vt2 = kNoSplit;      // odd encoder layers: with tile-level dependencies layer l+1 projects while layer l still attends
@@ -233,6 +234,17 @@ int make_linear_ln(cotr_model* m, const std::vector<float>& w, const std::vector
 }
 
 // backbone.py:46-56 folded into the conv: w' = w * s[o], shift = b - rm * s, s = weight * (rv + 1e-5)^-1/2.
+// [cout][7][7][3] (kh, kw, c) -> [cout][7][8][4]: the K order of A_STEM_NHWC4 (common.cuh), zero weights for pixel slot 7 / channel 3
+std::vector<float> stem_weight_order(const std::vector<float>& w, int cout) {
+    std::vector<float> o((size_t)cout * kStemK, 0.f);
+    for (int n = 0; n < cout; ++n)
+        for (int y = 0; y < 7; ++y)
+            for (int x = 0; x < 7; ++x)
+                for (int c = 0; c < 3; ++c)
+                    o[(size_t)n * kStemK + y * 32 + x * 4 + c] = w[(((size_t)n * 7 + y) * 7 + x) * 3 + c];
+    return o;
+}
+
 int make_conv(cotr_model* m, const TensorMap& tm, const std::string& conv, const std::string& bn,
               int cout, int cin, int kh, int kw, int stride, int pad, DevConv* out) {
     const cotr_tensor* w = tm.get(conv + ".weight", {cout, cin, kh, kw});
@@ -252,8 +264,12 @@ int make_conv(cotr_model* m, const TensorMap& tm, const std::string& conv, const
                         (float)((double)w->data[(((size_t)o * cin + c) * kh + y) * kw + x] * s);
     }
     out->cout = cout; out->cin = cin; out->kh = kh; out->kw = kw; out->stride = stride; out->pad = pad;
+    if (kh == 7 && cin == 3) {      // the stem reads the bordered NHWC4 canvas: K = (kh, 8 pixel slots, 4 channels), zeros in the padding
+        wf = stem_weight_order(wf, cout);
+        out->kw = 8; out->cin = 4; out->stem = true;
+    }
     if (upload(m, wf, &out->w)) return 1;
-    if (upload_tc(m, wf, cout, kh * kw * cin, &out->wtc, &out->wtc_scale)) return 1;
+    if (upload_tc(m, wf, cout, out->kh * out->kw * out->cin, &out->wtc, &out->wtc_scale)) return 1;
     if (upload(m, bf, &out->b)) return 1;
     return 0;
 }
@@ -343,7 +359,7 @@ inline int sync_tiles_for(int rows) {          // per-tile counters only while t
     return t <= kSyncBlockInts - 1 ? t : 0;
 }
 
-enum KernelId { K_GEMM_TC = 0, K_GEMM_SIMT = 1, K_ATTN_TC = 2, K_ATTN_SIMT = 3, K_LAYERNORM = 4, K_MAXPOOL = 5, K_QENC = 6 };
+enum KernelId { K_GEMM_TC = 0, K_GEMM_SIMT = 1, K_ATTN_TC = 2, K_ATTN_SIMT = 3, K_LAYERNORM = 4, K_MAXPOOL = 5, K_QENC = 6, K_STEM_CANVAS = 7 };
 
 // Counts the launch and, when the profiler is on, brackets it with two events on the launching stream.
 struct LaunchScope {
@@ -466,14 +482,12 @@ int run_linear_dln(const Run& r, const DevLinear& L, int M, CSplit16 A, int lda,
     return launch_tc(r, p, dep_mode);
 }
 
-int run_conv(const Run& r, const DevConv& c, int n_img, CSplit16 in, const float* in_f32, int H, int W, Split16 out,
-             bool relu, CSplit16 residual) {
-    const int OH = (H + 2 * c.pad - c.kh) / c.stride + 1;
-    const int OW = (W + 2 * c.pad - c.kw) / c.stride + 1;
+int run_conv(const Run& r, const DevConv& c, int n_img, CSplit16 in, int H, int W, Split16 out, bool relu, CSplit16 residual) {
+    const int OH = c.stem ? H / 2 : (H + 2 * c.pad - c.kh) / c.stride + 1;
+    const int OW = c.stem ? W / 2 : (W + 2 * c.pad - c.kw) / c.stride + 1;
     GemmParams p = gemm_base(n_img * OH * OW, c.cout, c.kh * c.kw * c.cin, in, c.cin, c.w, c.wtc, c.wtc_scale, out, c.cout);
-    if (in_f32) {
-        p.a_mode = A_STEM_NCHW;
-        p.a_f32 = in_f32;
+    if (c.stem) {
+        p.a_mode = A_STEM_NHWC4;        // `in` is the bordered canvas (launch_stem_canvas)
     } else if (c.kh == 1 && c.kw == 1 && c.stride == 1) {
         p.a_mode = A_ROWMAJOR;          // NHWC 1x1 convolution is a plain GEMM over pixels
     } else {
@@ -517,7 +531,7 @@ constexpr size_t kT2Elems = 64 * 64 * 64;          // largest conv2 output per i
 size_t encode_ws_elems(int B) {
     const size_t img = 2 * (size_t)B;
     const size_t tok = (size_t)B * kTokens;
-    return img * (kStemElems + 3 * kBigElems + kT1Elems + kT2Elems) + tok * (kDModel * 4 + 4 * kDModel + kFF) +
+    return img * (kStemCanvasElems + kStemElems + 3 * kBigElems + kT1Elems + kT2Elems) + tok * (kDModel * 4 + 4 * kDModel + kFF) +
            2 * (size_t)B * kVtLayer + tok * kDModel /* fp32 LN scratch */ + tok * 64 /* row statistics */;
 }
 size_t decode_ws_elems(int rows) {
@@ -595,7 +609,7 @@ int ensure_encode_ws(cotr_model* m, int B) {
     if (B <= w.cap_pairs) return 0;
     COTR_CHECK_CUDA(cudaDeviceSynchronize());
     drop_graphs(m);
-    Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh, &w.qk2, &w.vt2};
+    Split16* bufs[] = {&w.canvas, &w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh, &w.qk2, &w.vt2};
     for (Split16* b : bufs) ws_free(b);
     ws_free_f32(&w.ln_tmp);
     if (w.kvimg) { cudaFree(w.kvimg); w.kvimg = nullptr; }
@@ -603,7 +617,7 @@ int ensure_encode_ws(cotr_model* m, int B) {
     ws_free_f32(reinterpret_cast<float**>(&w.enc_st_a));
     ws_free_f32(reinterpret_cast<float**>(&w.enc_st_b));
     const size_t img = 2 * (size_t)B, tok = (size_t)B * kTokens;
-    if (ws_alloc(&w.stem, img * kStemElems) || ws_alloc(&w.bx, img * kBigElems) || ws_alloc(&w.by, img * kBigElems) ||
+    if (ws_alloc(&w.canvas, img * kStemCanvasElems) || ws_alloc(&w.stem, img * kStemElems) || ws_alloc(&w.bx, img * kBigElems) || ws_alloc(&w.by, img * kBigElems) ||
         ws_alloc(&w.bds, img * kBigElems) || ws_alloc(&w.bt1, img * kT1Elems) || ws_alloc(&w.bt2, img * kT2Elems) ||
         ws_alloc(&w.src, tok * kDModel) || ws_alloc(&w.xa, tok * kDModel) || ws_alloc(&w.xb, tok * kDModel) ||
         ws_alloc(&w.qk, tok * 2 * kDModel) || ws_alloc(&w.vt, (size_t)B * kVtLayer) || ws_alloc(&w.ao, tok * kDModel) ||
@@ -616,6 +630,8 @@ int ensure_encode_ws(cotr_model* m, int B) {
     // the 16 pad bytes of every value key group are copied by the bulk TMA: keep them defined
     COTR_CHECK_CUDA(cudaMemset(w.kvimg, 0, (size_t)B * kHeads * kAttnHeadImgBytes));
     COTR_CHECK_CUDA(cudaMemset(w.kvimg2, 0, (size_t)B * kHeads * kAttnHeadImgBytes));
+    // the border of the stem canvas is the convolution's zero padding: written here, never again
+    COTR_CHECK_CUDA(cudaMemset(w.canvas.hi, 0, img * kStemCanvasElems * 2 * sizeof(__half)));
     w.cap_pairs = B;
     return 0;
 }
@@ -662,7 +678,14 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
 
     // backbone.py:81-82: the two 256x256 halves go through the ResNet body as independent images.
     // Stem: conv 7x7/2 (+FrozenBN folded) + ReLU, then MaxPool 3x3/2  (torchvision resnet.py _forward_impl).
-    if (run_conv(r, m->stem, n_img, none, img, 256, 256, w.stem, true, none)) return 1;
+    {
+        LaunchScope scope(r, K_STEM_CANVAS, n_img * 256 * 256, 4, 0);
+        LaunchSync y = plan_dep(r, DEP_ALL, n_img * 256 * 256);
+        if (launch_stem_canvas(img, w.canvas, n_img, s, y)) return 1;
+        const size_t blocks = ((size_t)n_img * 256 * 256 + 255) / 256;
+        plan_done(r, y, (int)(blocks < 148 * 16 ? blocks : 148 * 16), 0, n_img * 256 * 256);
+    }
+    if (run_conv(r, m->stem, n_img, cs(w.canvas), 256, 256, w.stem, true, none)) return 1;
     {
         LaunchScope scope(r, K_MAXPOOL, n_img * 64 * 64, 64, 0);
         LaunchSync y = plan_dep(r, DEP_ALL, n_img * 64 * 64);
@@ -677,15 +700,15 @@ int encode_impl(cotr_model* m, const float* img, int B, cotr_context* ctx, cudaS
     int H = 64, W = 64;
     for (const Block& b : m->blocks) {
         // torchvision Bottleneck (v1.5): 1x1 -> 3x3(stride) -> 1x1, + identity | downsample, ReLU
-        if (run_conv(r, b.c1, n_img, cs(x), nullptr, H, W, w.bt1, true, none)) return 1;
-        if (run_conv(r, b.c2, n_img, cs(w.bt1), nullptr, H, W, w.bt2, true, none)) return 1;
+        if (run_conv(r, b.c1, n_img, cs(x), H, W, w.bt1, true, none)) return 1;
+        if (run_conv(r, b.c2, n_img, cs(w.bt1), H, W, w.bt2, true, none)) return 1;
         const int OH = H / b.c2.stride, OW = W / b.c2.stride;
         CSplit16 identity = cs(x);
         if (b.has_ds) {
-            if (run_conv(r, b.ds, n_img, cs(x), nullptr, H, W, w.bds, false, none)) return 1;
+            if (run_conv(r, b.ds, n_img, cs(x), H, W, w.bds, false, none)) return 1;
             identity = cs(w.bds);
         }
-        if (run_conv(r, b.c3, n_img, cs(w.bt2), nullptr, OH, OW, y, true, identity)) return 1;
+        if (run_conv(r, b.c3, n_img, cs(w.bt2), OH, OW, y, true, identity)) return 1;
         Split16 t = x; x = y; y = t;
         H = OH; W = OW;
     }
@@ -1183,7 +1206,7 @@ void cotr_destroy(cotr_model* m) {
     if (m->own_ctx) cotr_context_destroy(m->own_ctx);
     for (void* p : m->allocs) cudaFree(p);
     Workspace& w = m->ws;
-    Split16* bufs[] = {&w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh,
+    Split16* bufs[] = {&w.canvas, &w.stem, &w.bx, &w.by, &w.bt1, &w.bt2, &w.bds, &w.src, &w.xa, &w.xb, &w.qk, &w.vt, &w.ao, &w.ffh,
                        &w.qpos, &w.qp, &w.t, &w.qb, &w.dao, &w.dh, &w.hs, &w.hd1, &w.hd2, &w.t2, &w.qk2, &w.vt2};
     for (Split16* b : bufs) ws_free(b);
     if (w.sync_ctr) cudaFree(w.sync_ctr);
@@ -1538,8 +1561,20 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
     if (!dln) { p.ln_gamma = ln_gamma_dev; p.ln_beta = ln_beta_dev; }
     p.ldc = d->ldc;
     TmpSplit a16, res16, out16;
-    if (d->a_mode == A_STEM_NCHW) {
-        p.a_f32 = A_dev;
+    int K = d->K;
+    std::vector<float> w_stem;
+    if (d->a_mode == A_STEM_NHWC4) {
+        // the stem as the model runs it: A_dev is the fp32 (B,3,256,512) canvas, w_host [N][7][7][3]; the hook builds the
+        // bordered NHWC4 operand and the matching weight order (K = 224)
+        COTR_CHECK(d->K == 147 && d->OH == 128 && d->OW == 128 && d->M % (128 * 128) == 0, "cotr_test_gemm: the stem mode expects K = 147, 128 x 128 outputs per image");
+        const int n_img = d->M / (128 * 128);
+        if (a16.empty((size_t)n_img * kStemCanvasElems)) return 1;
+        COTR_CHECK_CUDA(cudaMemset(a16.t.hi, 0, (size_t)n_img * kStemCanvasElems * 2 * sizeof(__half)));
+        if (launch_stem_canvas(A_dev, a16.t, n_img, 0)) return 1;
+        p.a = cs(a16.t);
+        w_stem = stem_weight_order(std::vector<float>(w_host, w_host + (size_t)d->N * 147), d->N);
+        w_host = w_stem.data();
+        K = kStemK; p.K = K; p.KW = 8; p.C = 4;
     } else {
         COTR_CHECK(d->a_elems > 0, "cotr_test_gemm: a_elems missing");
         if (a16.from_f32(A_dev, (size_t)d->a_elems)) return 1;
@@ -1555,7 +1590,7 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
     float* wd = nullptr;
     void* wtc = nullptr;
     float* scratch = nullptr;
-    const size_t wn = (size_t)d->N * d->K;
+    const size_t wn = (size_t)d->N * K;
     COTR_CHECK_CUDA(cudaMalloc((void**)&wd, wn * sizeof(float)));
     COTR_CHECK_CUDA(cudaMemcpy(wd, w_host, wn * sizeof(float), cudaMemcpyHostToDevice));
     // deferred LayerNorm of A: the packed weights carry gamma, column sums and beta W^T + bias go to the epilogue
@@ -1601,9 +1636,9 @@ int cotr_test_gemm(const cotr_test_gemm_desc* d, const float* A_dev, const float
         COTR_CHECK(d->path == 0 && part_out_dev != nullptr && d->N == 256, "cotr_test_gemm: emit_part needs path 0, N = 256 and an output buffer");
         p.ln_part_out = reinterpret_cast<float2*>(part_out_dev);
     }
-    const size_t tcb = tc_weight_bytes(d->N, d->K);
+    const size_t tcb = tc_weight_bytes(d->N, K);
     std::vector<uint8_t> img(tcb);
-    p.acc_scale = tc_pack_weight(w_host, d->N, d->K, img.data());
+    p.acc_scale = tc_pack_weight(w_host, d->N, K, img.data());
     COTR_CHECK_CUDA(cudaMalloc(&wtc, tcb));
     COTR_CHECK_CUDA(cudaMemcpy(wtc, img.data(), tcb, cudaMemcpyHostToDevice));
     p.Wt = wd; p.Wtc = wtc;

@@ -81,7 +81,7 @@ def get_patch_centered_at(img, pos, scale=1.0, return_content=True, img_shape=No
     if img_shape is None:
         img_shape = img.shape
     h, w, _ = img_shape
-    scale = np.clip(scale, 0.0, 1.0)
+    scale = min(max(scale, 0.0), 1.0)          # np.clip on a scalar, without the array machinery (called ~10^5 times per run)
     size = min(h, w) * scale
     size = int((size // 2) * 2)
     top = int(pos[1] - size // 2)        # int() truncates toward zero, like the reference

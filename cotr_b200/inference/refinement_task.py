@@ -71,8 +71,9 @@ class RefinementTask():
 
     def _query_in(self, patch_from):
         # x is normalised by 2*w because the canvas is two patches wide (refinement_task.py:110)
-        rel = (np.array(self.loc_from) - np.array([patch_from.x, patch_from.y])) / np.array([patch_from.w * 2, patch_from.h])
-        return torch.from_numpy(rel)[None].float()
+        # the reference builds three small arrays here; the same two float64 divisions, rounded to fp32 the same way
+        return torch.tensor([[(self.loc_from[0] - patch_from.x) / (patch_from.w * 2), (self.loc_from[1] - patch_from.y) / patch_from.h]],
+                            dtype=torch.float32)
 
     def _submit(self, patch_from, patch_to, with_img_key):
         self.cur_job = {'patch_from': _geometry_only(patch_from), 'patch_to': _geometry_only(patch_to),

@@ -77,10 +77,12 @@ class SparseEngine():
         return self.model.preprocess_canvases(self._device_image(tasks[0].image_from), self._device_image(tasks[0].image_to), rects)
 
     # ---- batching ------------------------------------------------------------------------------------------
-    def form_batch(self, tasks, zoom=None):
-        """First `batch_size` open tasks (optionally at one zoom level) -> stacked canvases and queries (:25-45)."""
+    def form_batch(self, tasks, zoom=None, start=0):
+        """First `batch_size` open tasks (optionally at one zoom level) -> stacked canvases and queries (:25-45).
+        `start`: the caller knows that no task before this index is open (the scan is the same, only shorter)."""
         chosen = []
-        for t in tasks:
+        for i in range(start, len(tasks)):
+            t = tasks[i]
             if _is_open(t, zoom):
                 chosen.append(t)
                 if len(chosen) >= self.batch_size:
@@ -221,15 +223,24 @@ class SparseEngine():
 
     # ---- drivers -------------------------------------------------------------------------------------------
     def _single_query_loop(self, tasks, max_corrs, zoom=None):
+        """The reference rescans every task three times per batch (good / finished counts for its progress line and the
+        first-open search, :201-211, :25-45): quadratic in the task count.  Same decisions and the same printed lines here
+        from running counts and a cursor - inside this loop only the tasks of the current batch change state, and a
+        task that is not open (finished, already submitted, or at another zoom level) cannot become open again."""
+        num_g, num_f, start = self.num_good_tasks(tasks), self.num_finished_tasks(tasks), 0
         while True:
-            num_g = self.num_good_tasks(tasks)
-            print(f'{num_g} / {max_corrs} | {self.num_finished_tasks(tasks)} / {len(tasks)}')
-            task_ref, img_batch, query_batch = self.form_batch(tasks, zoom)
+            print(f'{num_g} / {max_corrs} | {num_f} / {len(tasks)}')
+            while start < len(tasks) and not _is_open(tasks[start], zoom):
+                start += 1
+            task_ref, img_batch, query_batch = self.form_batch(tasks, zoom, start)
             if len(task_ref) == 0 or num_g >= max_corrs:
                 break
             out = self.infer_batch(img_batch, query_batch)
             for t, o in zip(task_ref, out):
                 t.step(o)
+                if t.status == 'finished':
+                    num_f += 1
+                    num_g += t.result == 'good'
 
     def _finish(self, tasks, max_corrs, return_idx, force, return_tasks_only, img_a_shape, img_b_shape):
         if return_tasks_only:
@@ -302,8 +313,8 @@ class FasterSparseEngine(SparseEngine):
         points, ids = [], []
         for i, t in enumerate(tasks):
             if _is_open(t, zoom):
-                info = t.peek()
-                points.append(np.concatenate([info['loc_from'], info['loc_to']]))
+                # what peek() reports as loc_from / loc_to (refinement_task.py:59-69) without building its two patches
+                points.append(np.concatenate([t.loc_from, t.cur_loc_to]))
                 ids.append(i)
         return np.array(points), np.array(ids)
 

@@ -172,7 +172,7 @@ int cotr_last_launch_count(const cotr_model* m);
  * by two CUDA events recorded on the launching stream.  cotr_profile_end synchronises the device, fills `out` with
  * one record per launch in launch order and returns -(count + 1) on success (so 0 records -> -1), > 0 on failure.
  * kernel ids: 0 gemm_tc (tcgen05), 1 gemm_simt, 2 attention_tc, 3 attention_simt, 4 layernorm, 5 maxpool,
- * 6 query_encode.  For GEMMs M,N,K are the problem size; for attention M = query rows, N = 512, K = 256. */
+ * 6 query_encode, 7 stem_canvas.  For GEMMs M,N,K are the problem size; for attention M = query rows, N = 512, K = 256. */
 typedef struct cotr_launch_record {
     int32_t kernel;
     int32_t M, N, K;
@@ -195,7 +195,7 @@ int cotr_set_gemm_path(cotr_model* m, int path);
 typedef struct cotr_test_gemm_desc {
     int32_t path;                 /* 0 = tcgen05, 1 = fp32 SIMT                                               */
     int32_t M, N, K;
-    int32_t a_mode;               /* 0 row-major [M,K]; 1 implicit im2col over NHWC; 2 stem NCHW canvas; 3 token gather */
+    int32_t a_mode;               /* 0 row-major [M,K]; 1 implicit im2col over NHWC; 2 7x7/2 stem (A_dev = the fp32 (B,3,256,512) canvas, w_host [N][7][7][3]); 3 token gather */
     int32_t lda;
     int32_t H, W, C, OH, OW, KH, KW, stride, pad;   /* convolution geometry for a_mode 1 / 2                  */
     int32_t relu;
