@@ -138,9 +138,11 @@ def config_dict(world):
             "parallelism": f"dp{world} (independent pairs)",
             "l2": "GPU arm: flushed between timed steps by writing a 256 MiB buffer; CPU arm: not applicable",
             "weights": "seeded synthetic (cotr_b200/utils/synthetic.py seed 0)",
-            "result_gather": "GPU arm, N > 1: nccl all_gather of the (N,1024,2) predictions issued every step on a side stream "
-                             "(cotr_b200.inference.sharding.AsyncGather: overlaps the next step, joined before the closing barrier; the "
-                             "synchronous gather is inside `e2e`); CPU arm (rank 0 runs one pair per step on the host cores): none"}
+            "result_gather": "GPU arm, N > 1: every step hands its (1,1024,2) block to the result exchange on a side stream "
+                             "(cotr_b200.inference.sharding.AsyncGather: peer-memory push over NVLink on one node, NCCL all_gather "
+                             "otherwise; overlaps the next step, joined before the closing barrier; the synchronous push + wait is "
+                             "inside `e2e`; the transport used is reported in `result_exchange`); CPU arm (rank 0 runs one pair per "
+                             "step on the host cores): none"}
 
 
 def committed_traffic():
