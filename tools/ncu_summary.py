@@ -23,7 +23,8 @@ def family(name):
     if m:
         mode = {"0": "row-major", "1": "3x3 conv", "2": "7x7 stem"}[m.group(3)]
         return f"gemm_tc<{m.group(1)}{', LN' if m.group(2) == '1' else ''}, {mode}{', DLN' if m.group(4) == '1' else ''}>"
-    for key in ("attention_tc_kernel", "layernorm256_twice", "layernorm256", "maxpool", "query_encode", "gemm_simt", "attention_simt"):
+    for key in ("attention_tc_kernel", "layernorm256_twice", "layernorm256", "ln_partials", "stem_canvas", "maxpool", "query_encode", "gemm_simt",
+                "attention_simt", "f32_to_split16", "split16_to_f32", "exchange_push", "exchange_wait"):
         if key in name:
             return key
     return re.sub(r"\(.*", "", name.split("::")[-1])[:40]
