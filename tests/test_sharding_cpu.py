@@ -107,3 +107,34 @@ def test_sharded_engines_equal_unsharded_gloo():
         assert all(results[r][0]), results[r][0]
     # every context of the (last) engine run was processed once across the ranks, and no rank did all of them
     assert 0 < results[0][1] and 0 < results[1][1]
+
+
+def _exchange_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cotr_b200.inference.sharding import open_exchange
+    # no CUDA device here: every rank must come back with the same answer ("no peer transport"), without hanging or raising
+    results[rank] = open_exchange(8192, torch.device("cpu")) is None and open_exchange(8200, torch.device("cpu")) is None
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_declines_collectively_without_cuda():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_exchange_worker, args=(world, port, results), nprocs=world, join=True)
+        assert dict(results) == {0: True, 1: True}
+
+
+def test_engine_bench_compares_survivor_sets():
+    """tools/engine_bench.compare_runs: overlap and differences of two runs whose survivors differ near the cut."""
+    import numpy as np
+    from tools.engine_bench import compare_runs
+    a = np.array([[1., 1., 5., 5.], [2., 2., 6., 6.], [3., 3., 7., 7.]])
+    b = np.array([[2., 2., 6., 6.5], [1., 1., 5., 5.], [9., 9., 0., 0.]])
+    r = compare_runs(a, b)
+    assert r["same_source_points"] is False and r["common_source_points"] == 2 and r["of"] == 3
+    assert r["max_abs_diff_px"] == 0.5 and r["median_abs_diff_px"] == 0.25
+    assert compare_runs(a, a.copy())["same_source_points"] is True
