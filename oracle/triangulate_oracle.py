@@ -5,7 +5,9 @@ OpenGL (vispy) rasterise the triangles with the target coordinates as vertex col
 triangle receives the barycentric interpolation of its three target points; pixels outside the hull stay 0.  vispy /
 GL are not available offline, so the restatement evaluates exactly that definition with scipy's own point location
 (`find_simplex` + the simplices' affine transforms) in float64.  "parity unpinned": the reference's tests hold no
-vectors for this function and its GL path cannot run here; the definition above is what is checked.
+vectors for this function and its GL path cannot run here; the definition above is what is checked, and
+tests/test_triangulate_cpu.py holds this restatement against scipy's LinearNDInterpolator (an independent
+implementation of the same definition) and against exact affine maps.
 """
 import numpy as np
 from scipy.spatial import Delaunay
