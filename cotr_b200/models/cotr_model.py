@@ -14,7 +14,6 @@ Unlike the reference constructor (backbone.py:106 `pretrained=True`) nothing is 
 """
 import math
 
-import numpy as np
 import torch
 from torch import nn
 
@@ -228,27 +227,7 @@ class COTR(nn.Module):
     def forward(self, samples, queries):
         x = self._canvas(samples)
         q = self._queries(queries, x.shape[0])
-        self._last_shape = (int(x.shape[0]), int(q.shape[1]))
         return {'pred_corrs': self.native().forward(x, q)}
-
-    @torch.no_grad()
-    def activation_peaks(self):
-        """max |activation| at the checkpoints of the LAST forward that the library keeps readable (backbone output, projected
-        tokens, encoder output, decoder output of the last chunk).  The split16 storage of activations clamps at +-65504
-        per plane without producing inf / NaN (csrc/split16.cuh), so a checkpoint whose statistics put a peak near that
-        value would lose information silently - this is the check to run once on a new checkpoint (debug call: it
-        synchronises the device and copies the buffers to the host)."""
-        pairs, q = getattr(self, '_last_shape', (0, 0))
-        if pairs == 0:
-            raise RuntimeError("activation_peaks: no forward has run on this model yet")
-        nat = self.native()
-        sizes = {'feat': pairs * 2 * 16 * 16 * 1024, 'src': pairs * 512 * 256, 'mem': pairs * 512 * 256, 'hs': min(pairs * q, 32768) * 256}
-        peaks = {}
-        for name, n in sizes.items():
-            v = nat.debug_read(name, n)
-            peaks[name] = float(np.abs(v).max()) if v.size else 0.0
-        peaks['headroom'] = 65504.0 / max(max(peaks.values()), 1e-30)
-        return peaks
 
     # ---- extensions used by cotr_b200.inference ---------------------------------------------------------
     supports_device_preprocess = True

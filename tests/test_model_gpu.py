@@ -204,19 +204,3 @@ def test_experimental_schedules_match_the_reference(golden_dir, built_lib, varia
                 assert model.native().last_launch_count() == (136 if variant == (1 << 16) else 112)
     finally:
         capi.lib().cotr_debug_set_variant(0)
-
-
-def test_activation_peaks_report_the_split16_headroom(default_model, golden_dir):
-    """`COTR.activation_peaks()`: the diagnostic for the storage format's silent clamp at +-65504 (csrc/split16.cuh).  The
-    seeded fixture stays far below it; the large-activation fixture (stem gain x30) moves the backbone peak up accordingly."""
-    img, queries = fixtures.make_inputs(1, 2, 64)
-    default_model(torch.from_numpy(img).cuda(), torch.from_numpy(queries).cuda())
-    peaks = default_model.activation_peaks()
-    assert set(peaks) == {"feat", "src", "mem", "hs", "headroom"}
-    assert all(0.0 < peaks[k] < 65504.0 for k in ("feat", "src", "mem", "hs"))
-    assert peaks["headroom"] > 10.0
-    _, sd, img_b, queries_b, _ = _case(golden_dir, "model_bigact_b1_q256")
-    big = _build(sd)
-    big(torch.from_numpy(img_b).cuda(), torch.from_numpy(queries_b).cuda())
-    peaks_big = big.activation_peaks()
-    assert peaks_big["feat"] > 3.0 * peaks["feat"] and peaks_big["headroom"] > 1.0
