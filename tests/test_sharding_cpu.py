@@ -138,3 +138,14 @@ def test_engine_bench_compares_survivor_sets():
     assert r["same_source_points"] is False and r["common_source_points"] == 2 and r["of"] == 3
     assert r["max_abs_diff_px"] == 0.5 and r["median_abs_diff_px"] == 0.25
     assert compare_runs(a, a.copy())["same_source_points"] is True
+
+
+def test_async_gather_is_transparent_on_one_rank():
+    """Without a process group (one GPU) `AsyncGather` hands the block straight back: no streams, no exchange."""
+    from cotr_b200.inference.sharding import AsyncGather
+    g = AsyncGather((1, 4, 2), torch.device("cpu"))
+    assert g.backend == "local" and g.exchange is None and g.side is None
+    pred = torch.arange(8, dtype=torch.float32).view(1, 4, 2)
+    g.submit(pred)
+    assert g.wait() is pred and g.check() == 0
+    g.close()
